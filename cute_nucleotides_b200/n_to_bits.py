@@ -1,0 +1,113 @@
+"""Host-side mirror of the reference module `cute_nucleotides::n_to_bits` (src/n_to_bits.rs).
+
+The reference's operator API is a naming family -- `n_to_bits_<variant>(n) -> Vec<u64>` and
+`bits_to_n_<variant>(bits, len) -> Vec<u8>`; a new backend is a new suffix.  This module adds the
+`_cuda` suffix with the same argument meaning and error behaviour:
+
+    n_to_bits_cuda(n)            mirrors  pub fn n_to_bits_lut(n: &[u8]) -> Vec<u64>            (:34)
+    bits_to_n_cuda(bits, len)    mirrors  pub fn bits_to_n_lut(bits: &[u64], len) -> Vec<u8>    (:51)
+
+plus the device-resident pair used for the roofline runs (torch tensors already in HBM).  Every call
+goes through the C ABI (include/cute_nucleotides_cuda.h); there is no CPU path here.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import LengthError, check
+
+__all__ = [
+    "n_to_bits_cuda", "bits_to_n_cuda", "words_for_len",
+    "encode_device", "decode_device", "generate_device", "generate_words_device", "LengthError",
+]
+
+
+def words_for_len(length: int) -> int:
+    """ceil(len / 32), the number of u64 words an encoder returns (src/n_to_bits.rs:35)."""
+    return (length >> 5) + (1 if length & 31 else 0)
+
+
+def _as_u8(n) -> np.ndarray:
+    if isinstance(n, np.ndarray):
+        if n.dtype != np.uint8:
+            raise TypeError("nucleotides must be bytes or a uint8 array")
+        return n if n.flags.c_contiguous else np.ascontiguousarray(n)
+    return np.frombuffer(n, dtype=np.uint8)   # bytes / bytearray / memoryview, zero-copy, any alignment
+
+
+def n_to_bits_cuda(n) -> np.ndarray:
+    """Encode ASCII {A,C,G,T/U} (any case) to 2-bit codes, 32 per u64.  Returns a uint64 array."""
+    src = _as_u8(n)
+    out = np.empty(words_for_len(src.size), dtype=np.uint64)   # caller-allocated, like Vec::with_capacity
+    if src.size:
+        check(_lib.load().cn_n_to_bits_host(src.ctypes.data, src.size, out.ctypes.data))
+    return out
+
+
+def bits_to_n_cuda(bits, length: int) -> bytes:
+    """Decode `length` nucleotides from packed words.  Raises LengthError where the reference panics."""
+    words = np.ascontiguousarray(bits, dtype=np.uint64)
+    if length < 0:
+        raise ValueError("length must be non-negative")
+    out = np.empty(length, dtype=np.uint8)
+    # the length check lives in C as well (status CN_ERR_LENGTH), so the panic text comes from one place
+    check(_lib.load().cn_bits_to_n_host(words.ctypes.data, words.size, length, out.ctypes.data))
+    return out.tobytes()
+
+
+# ---- device-resident API (torch tensors; torch is plumbing for memory and streams only) -------------
+
+def _stream_ptr(stream) -> int:
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return s.cuda_stream
+
+
+def encode_device(n, out=None, stream=None):
+    """n: uint8 CUDA tensor of ASCII nucleotides -> int64 CUDA tensor of ceil(len/32) packed words
+    (bit pattern of the reference's u64s; torch has no general uint64 kernels, so the carrier is int64)."""
+    import torch
+    if n.dtype != torch.uint8 or not n.is_cuda or not n.is_contiguous():
+        raise TypeError("encode_device expects a contiguous uint8 CUDA tensor")
+    length = n.numel()
+    if out is None:
+        out = torch.empty(words_for_len(length), dtype=torch.int64, device=n.device)
+    elif out.numel() < words_for_len(length) or out.element_size() != 8 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous 8-byte-element tensor with ceil(len/32) elements")
+    with torch.cuda.device(n.device):
+        check(_lib.load().cn_encode_device(n.data_ptr(), length, out.data_ptr(), _stream_ptr(stream)))
+    return out
+
+
+def decode_device(bits, length: int, out=None, stream=None):
+    """bits: 8-byte-element CUDA tensor of packed words -> uint8 CUDA tensor of `length` ASCII bytes."""
+    import torch
+    if bits.element_size() != 8 or not bits.is_cuda or not bits.is_contiguous():
+        raise TypeError("decode_device expects a contiguous int64/uint64 CUDA tensor")
+    if out is None:
+        if length > bits.numel() * 32:
+            raise LengthError(_lib.CN_ERR_LENGTH, _lib.load().cn_length_panic_message().decode())
+        out = torch.empty(length, dtype=torch.uint8, device=bits.device)
+    elif out.numel() < length or out.dtype != torch.uint8 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous uint8 tensor with at least `length` elements")
+    with torch.cuda.device(bits.device):
+        check(_lib.load().cn_decode_device(bits.data_ptr(), bits.numel(), length, out.data_ptr(), _stream_ptr(stream)))
+    return out
+
+
+def generate_device(out, offset: int, seed: int, alphabet: int = 4, stream=None):
+    """Fill a uint8 CUDA tensor with the shared synthetic sequence (global nucleotide index offset+i)."""
+    import torch
+    with torch.cuda.device(out.device):
+        check(_lib.load().cn_generate_device(out.data_ptr(), offset, out.numel(), seed, alphabet, _stream_ptr(stream)))
+    return out
+
+
+def generate_words_device(out, first_word: int, seed: int, stream=None):
+    import torch
+    with torch.cuda.device(out.device):
+        check(_lib.load().cn_generate_words_device(out.data_ptr(), first_word, out.numel(), seed, _stream_ptr(stream)))
+    return out

@@ -1,0 +1,78 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol the header declares
+(and nothing else), and refuses to compute without a GPU instead of falling back."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "cute_nucleotides_cuda.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    return sorted(set(re.findall(r"^CN_API\s+[\w\s\*]+?\b(cn_\w+)\s*\(", text, flags=re.M)))
+
+
+def test_header_declares_the_path():
+    syms = declared_symbols()
+    for must in ("cn_n_to_bits_host", "cn_bits_to_n_host", "cn_encode_device", "cn_decode_device", "cn_last_error"):
+        assert must in syms
+
+
+def test_library_exports_exactly_the_header(cn):
+    from cute_nucleotides_b200 import _lib
+    lib = _lib.load()
+    syms = declared_symbols()
+    assert sorted(_lib.PROTOTYPES) == syms          # the Python binding covers the whole header
+    for s in syms:
+        assert hasattr(lib, s), s
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = sorted(line.split()[-1] for line in out.splitlines() if " T " in line)
+    assert exported == syms, "the library must export the header's symbols and nothing else (no leaked cudart)"
+
+
+def test_pure_host_entry_points(cn):
+    from cute_nucleotides_b200 import _lib
+    lib = _lib.load()
+    assert lib.cn_abi_version() == _lib.ABI_VERSION
+    for length in (0, 1, 31, 32, 33, 64, 65, 10 * (1 << 30), 10 * (1 << 30) + 1):
+        assert lib.cn_words_for_len(length) == (length + 31) // 32 == cn.words_for_len(length)
+    assert lib.cn_length_panic_message() == b"The length is greater than the number of nucleotides!"
+    assert lib.cn_set_tuning(0, 16, 4, 256) == 0
+    assert lib.cn_set_tuning(0, 24, 4, 256) == _lib.CN_ERR_ARG and b"unsupported" in lib.cn_last_error()
+
+
+def test_length_check_needs_no_gpu(cn):
+    # len > 32*nwords is rejected before any CUDA call, with the reference's panic text (src/n_to_bits.rs:52-54)
+    with pytest.raises(cn.LengthError, match="The length is greater than the number of nucleotides!"):
+        cn.bits_to_n_cuda(np.zeros(2, dtype=np.uint64), 65)
+
+
+def test_empty_inputs_need_no_gpu(cn):
+    assert cn.n_to_bits_cuda(b"").size == 0
+    assert cn.bits_to_n_cuda(np.zeros(0, dtype=np.uint64), 0) == b""
+    assert cn.bits_to_n_cuda(np.zeros(3, dtype=np.uint64), 0) == b""
+
+
+def test_no_cpu_fallback_without_a_gpu(cn):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the -m gpu tests")
+    from cute_nucleotides_b200._lib import CuteNucleotidesError
+    with pytest.raises(CuteNucleotidesError) as e:
+        cn.n_to_bits_cuda(b"ATCG")
+    assert e.value.code == 2      # CN_ERR_CUDA: loud failure, not a silent CPU result
+    with pytest.raises(CuteNucleotidesError):
+        cn.bits_to_n_cuda(np.array([0xD8], dtype=np.uint64), 4)
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "cute_nucleotides_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert "libcn_oracle" not in text and "cn_oracle" not in text and "oracle_" not in text, fn

@@ -1,0 +1,312 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`).  Every product call goes through the C ABI
+(include/cute_nucleotides_cuda.h) via cute_nucleotides_b200; the oracle is only the checker.
+
+Bar: bit-exact (integer/byte work).  Layout mirrors the reference's own tests (src/n_to_bits.rs:408-470):
+known-answer vectors first, then the cases the reference never exercises (SURVEY section 4 "gaps"):
+lower case, U, body+tail lengths, truncating len, the len panic, empty input, unaligned slices, > 4 GiB.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+with open(os.path.join(ROOT, "tests", "golden", "kat.json")) as f:
+    GOLD = json.load(f)
+
+SIZES = [1, 3, 4, 5, 15, 16, 17, 31, 32, 33, 47, 48, 49, 63, 64, 65, 127, 128, 129, 255, 1000, 4095, 4096, 4097,
+         16383, 40000, 65536 + 17, (1 << 20), (1 << 20) + 17, 3 * (1 << 20) + 5]
+TUNINGS = [(v, u, t) for v in (16, 32) for u in (1, 2, 4, 8) for t in (128, 256, 512)]
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a GPU; there is no CPU fallback to test"
+    torch.cuda.set_device(0)
+    return torch
+
+
+@pytest.fixture(autouse=True)
+def default_tuning(cn):
+    from cute_nucleotides_b200 import _lib
+    lib = _lib.load()
+    saved = []
+    for d in (0, 1):
+        import ctypes
+        v, u, t = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        lib.cn_get_tuning(d, ctypes.byref(v), ctypes.byref(u), ctypes.byref(t))
+        saved.append((d, v.value, u.value, t.value))
+    yield
+    for d, v, u, t in saved:
+        lib.cn_set_tuning(d, v, u, t)
+    lib.cn_set_host_strategy(0, 16 << 20)
+
+
+def to_np_u64(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's own known-answer tests, through the drop-in signatures
+# ---------------------------------------------------------------------------------------------------
+def test_reference_kat_encode(cn):
+    for case in GOLD["encode"]:                      # src/n_to_bits.rs:414-416 (and :427-450)
+        got = cn.n_to_bits_cuda(case["input"].encode())
+        assert got.dtype == np.uint64 and [str(int(x)) for x in got] == case["words"]
+
+
+def test_reference_kat_decode(cn):
+    for case in GOLD["decode"]:                      # src/n_to_bits.rs:421-422 (and :455-468)
+        words = np.array([int(w) for w in case["words"]], dtype=np.uint64)
+        assert cn.bits_to_n_cuda(words, case["len"]) == case["output"].encode()
+
+
+def test_reference_bench_fixture(cn):
+    fx = GOLD["bench_fixture"]                       # benches/bench_n_to_bits.rs:68-78
+    n = (fx["unit"] * fx["repeat"]).encode()
+    words = cn.n_to_bits_cuda(n)
+    assert words.size == fx["nwords"] and np.all(words == np.uint64(int(fx["every_word"])))
+    assert cn.bits_to_n_cuda(words, len(n)) == n
+
+
+def test_length_panic(cn):
+    with pytest.raises(cn.LengthError, match=GOLD["panic_text"]):
+        cn.bits_to_n_cuda(np.zeros(2, dtype=np.uint64), 65)
+    assert cn.bits_to_n_cuda(np.zeros(2, dtype=np.uint64), 64) == b"A" * 64
+
+
+def test_empty(cn, torch_cuda):
+    torch = torch_cuda
+    assert cn.n_to_bits_cuda(b"").size == 0
+    assert cn.bits_to_n_cuda(np.zeros(0, dtype=np.uint64), 0) == b""
+    e = cn.encode_device(torch.empty(0, dtype=torch.uint8, device="cuda"))
+    assert e.numel() == 0
+    d = cn.decode_device(torch.empty(4, dtype=torch.int64, device="cuda"), 0)
+    assert d.numel() == 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# host-slice path (the literal drop-in) vs the scalar oracle
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("size", SIZES)
+def test_host_encode_decode_vs_oracle(cn, oracle, size):
+    n = oracle.generate(size, seed=size, alphabet=10)            # mixed case with U
+    ref = oracle.n_to_bits(n, "lut")
+    got = cn.n_to_bits_cuda(n)
+    assert np.array_equal(got, ref)
+    assert cn.bits_to_n_cuda(got, size) == oracle.bits_to_n(ref, size, "lut") == oracle.canonical(n)
+    # truncating len: fewer nucleotides than the words hold
+    for shorter in {size - 1, size // 2, max(size - 33, 0)}:
+        if shorter >= 0:
+            assert cn.bits_to_n_cuda(got, shorter) == oracle.bits_to_n(ref, shorter, "lut")
+
+
+@pytest.mark.parametrize("offset", [1, 2, 3, 5, 8, 13, 15])
+def test_host_unaligned_slices(cn, oracle, offset):
+    base = oracle.generate(100000 + offset, seed=77, alphabet=10)
+    n = base[offset:]                                            # a &[u8] can start anywhere
+    assert np.array_equal(cn.n_to_bits_cuda(n), oracle.n_to_bits(n, "lut"))
+    words = oracle.n_to_bits(n, "lut")
+    buf = np.empty(n.size + offset, dtype=np.uint8)
+    assert cn.bits_to_n_cuda(words, n.size) == oracle.canonical(n)
+
+
+@pytest.mark.parametrize("strategy,chunk", [(0, 4096), (0, 1 << 16), (1, 4096), (1, 1 << 20)])
+def test_host_pipeline_chunking(cn, oracle, strategy, chunk):
+    """Many small chunks through the slot ring (wrap-around, ragged last chunk), both strategies."""
+    from cute_nucleotides_b200 import _lib
+    assert _lib.load().cn_set_host_strategy(strategy, chunk) == 0
+    for size in (chunk * 9 + 17, chunk * 4, chunk - 1, 5):
+        n = oracle.generate(size, seed=size ^ 0x55, alphabet=10)
+        ref = oracle.n_to_bits(n, "lut")
+        got = cn.n_to_bits_cuda(n)
+        assert np.array_equal(got, ref)
+        assert cn.bits_to_n_cuda(got, size) == oracle.canonical(n)
+
+
+def test_host_pinned_buffers(cn, oracle, torch_cuda):
+    """Pinned caller buffers take the direct-DMA / zero-copy branches of the host pipeline."""
+    torch = torch_cuda
+    from cute_nucleotides_b200 import _lib
+    lib = _lib.load()
+    size = (1 << 22) + 1234
+    n = oracle.generate(size, seed=9, alphabet=10)
+    ref = oracle.n_to_bits(n, "lut")
+    src = torch.from_numpy(n).pin_memory()
+    out = torch.empty(ref.size, dtype=torch.int64).pin_memory()
+    dec = torch.empty(size, dtype=torch.uint8).pin_memory()
+    for strategy in (0, 1):
+        assert lib.cn_set_host_strategy(strategy, 1 << 20) == 0
+        out.zero_(); dec.zero_()
+        _lib.check(lib.cn_n_to_bits_host(src.data_ptr(), size, out.data_ptr()))
+        assert np.array_equal(out.numpy().view(np.uint64), ref)
+        _lib.check(lib.cn_bits_to_n_host(out.data_ptr(), ref.size, size, dec.data_ptr()))
+        assert dec.numpy().tobytes() == oracle.canonical(n)
+        # unaligned pinned sub-slices
+        _lib.check(lib.cn_n_to_bits_host(src.data_ptr() + 3, size - 3, out.data_ptr()))
+        assert np.array_equal(out.numpy().view(np.uint64)[: (size - 3 + 31) // 32], oracle.n_to_bits(n[3:], "lut"))
+        _lib.check(lib.cn_bits_to_n_host(out.data_ptr(), (size - 3 + 31) // 32, size - 3, dec.data_ptr() + 5))
+        assert dec.numpy()[5 : 5 + size - 3].tobytes() == oracle.canonical(n[3:])
+
+
+# ---------------------------------------------------------------------------------------------------
+# device-resident path vs the oracle, across every kernel configuration the library can select
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("vec,unroll,threads", TUNINGS)
+def test_device_all_tunings(cn, oracle, torch_cuda, vec, unroll, threads):
+    torch = torch_cuda
+    from cute_nucleotides_b200 import _lib
+    lib = _lib.load()
+    assert lib.cn_set_tuning(0, vec, unroll, threads) == 0 and lib.cn_set_tuning(1, vec, unroll, threads) == 0
+    tile = vec * unroll * threads
+    for size in (1, 31, 33, tile - 1, tile, tile + 1, 3 * tile + 37, (1 << 20) + 17):
+        n = oracle.generate(size, seed=size + vec, alphabet=10)
+        ref = oracle.n_to_bits(n, "lut")
+        d_n = torch.from_numpy(n).cuda()
+        d_bits = cn.encode_device(d_n)
+        assert np.array_equal(to_np_u64(d_bits), ref), (size,)
+        d_out = cn.decode_device(d_bits, size)
+        assert d_out.cpu().numpy().tobytes() == oracle.canonical(n), (size,)
+
+
+@pytest.mark.parametrize("in_off", [0, 1, 4, 7, 9, 15, 16, 17])
+@pytest.mark.parametrize("size", [0, 1, 14, 15, 16, 17, 31, 32, 33, 50, 4096, 100003])
+def test_device_unaligned_pointers(cn, oracle, torch_cuda, in_off, size):
+    torch = torch_cuda
+    from cute_nucleotides_b200 import _lib
+    lib = _lib.load()
+    n = oracle.generate(size + 64, seed=size * 31 + in_off, alphabet=10)
+    d_all = torch.from_numpy(n).cuda()
+    sl = n[in_off : in_off + size]
+    ref = oracle.n_to_bits(sl, "lut")
+    d_bits = torch.full((ref.size + 1,), -1, dtype=torch.int64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.cn_encode_device(d_all.data_ptr() + in_off, size, d_bits.data_ptr(), stream))
+    got = to_np_u64(d_bits)
+    assert np.array_equal(got[: ref.size], ref)
+    assert got[ref.size] == np.uint64(0xFFFFFFFFFFFFFFFF)        # nothing written past ceil(len/32) words
+    # decode into an unaligned destination, with guard bytes on both sides
+    d_out = torch.full((size + 64,), 0x7E, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.cn_decode_device(d_bits.data_ptr(), ref.size, size, d_out.data_ptr() + in_off, stream))
+    h = d_out.cpu().numpy()
+    assert h[in_off : in_off + size].tobytes() == oracle.canonical(sl)
+    assert np.all(h[:in_off] == 0x7E) and np.all(h[in_off + size :] == 0x7E)
+
+
+def test_device_decode_arbitrary_words_vs_oracle(cn, oracle, torch_cuda):
+    """BASELINE config 4 shape at small scale: any bit pattern is a valid packed word."""
+    torch = torch_cuda
+    nwords = (1 << 18) + 3
+    words = oracle.generate_words(nwords, seed=4)
+    d_bits = torch.from_numpy(words.view(np.int64)).cuda()
+    for length in (32 * nwords, 32 * nwords - 1, 32 * nwords - 31, 32 * (nwords - 1) + 1, 12345):
+        got = cn.decode_device(d_bits, length).cpu().numpy().tobytes()
+        assert got == oracle.decode_mt(words, length, "lut").tobytes()
+    with pytest.raises(cn.LengthError, match=GOLD["panic_text"]):
+        cn.decode_device(d_bits, 32 * nwords + 1)
+
+
+def test_device_generator_matches_host_generator(cn, oracle, torch_cuda):
+    torch = torch_cuda
+    for alphabet in (4, 10):
+        for size, offset in ((1, 0), (7, 8), (100003, 0), (65536, 40000)):
+            d = cn.generate_device(torch.empty(size, dtype=torch.uint8, device="cuda"), offset, 0xC0FFEE, alphabet)
+            assert np.array_equal(d.cpu().numpy(), oracle.generate(size, 0xC0FFEE, alphabet, offset))
+    w = cn.generate_words_device(torch.empty(1000, dtype=torch.int64, device="cuda"), 17, 99)
+    assert np.array_equal(to_np_u64(w), oracle.generate_words(1000, 99, first_word=17))
+
+
+def test_invalid_bytes_follow_the_simd_encoders(cn, oracle):
+    """Outside the alphabet the kernel computes (b >> 1) & 3 like the reference's pext/shift/movemask/mul
+    body (src/n_to_bits.rs:85,100); documented, not parity-relevant (SURVEY 8a notes)."""
+    n = np.arange(128, dtype=np.uint8).repeat(32)              # every 7-bit byte, one word each
+    got = cn.n_to_bits_cuda(n)
+    if oracle.simd_ok:
+        assert np.array_equal(got, oracle.n_to_bits(n, "mul"))
+    codes = (np.arange(128) >> 1) & 3
+    expect = np.array([sum(int(c) << (2 * k) for k in range(32)) for c in codes], dtype=np.uint64)
+    assert np.array_equal(got, expect)
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE configs at full size
+# ---------------------------------------------------------------------------------------------------
+def test_config2_one_gib_bit_exact(cn, oracle, torch_cuda):
+    """BASELINE config 2: 1 GiB random ACGT, encode + decode on one B200, bit-exact vs n_to_bits_lut
+    on the identical host-generated buffer (all 2^25 words), decoded output equals the input."""
+    torch = torch_cuda
+    size = 1 << 30
+    n = oracle.generate(size, seed=0xC0FFEE, alphabet=4)
+    d_n = cn.generate_device(torch.empty(size, dtype=torch.uint8, device="cuda"), 0, 0xC0FFEE, 4)
+    assert np.array_equal(d_n[: 1 << 24].cpu().numpy(), n[: 1 << 24])
+    d_bits = cn.encode_device(d_n)
+    ref = oracle.encode_mt(n, "lut")
+    assert d_bits.numel() == 1 << 25
+    assert np.array_equal(to_np_u64(d_bits), ref)
+    d_out = cn.decode_device(d_bits, size)
+    assert torch.equal(d_out, d_n)                                # alphabet 4 is already canonical
+    assert np.array_equal(d_out.cpu().numpy(), n)
+
+
+def _fold(t):
+    """order-sensitive 64-bit checksum of a CUDA tensor's bytes, computed on device with torch"""
+    import torch
+    v = t.view(torch.int64) if t.dtype != torch.int64 else t
+    idx = torch.arange(v.numel(), device=v.device, dtype=torch.int64)
+    return int(((v ^ (idx * -7046029254386353131)) * 0x100000001B3).sum().item())   # wraps mod 2^64
+
+
+def test_config3_config4_ten_gib_properties(cn, oracle, torch_cuda):
+    """BASELINE configs 3 and 4 at full size (10 GiB, mixed case with U; > 4 GiB exercises 64-bit indexing).
+    Size-independent properties: (i) sampled windows are bit-exact vs the oracle, including windows that
+    straddle the 4 GiB and 8 GiB boundaries and the ragged end; (ii) decode(encode(x)) == canonical(x)
+    over the whole buffer; (iii) encode is shard-linear: encoding a window alone gives the same words
+    (checksum of checksums)."""
+    torch = torch_cuda
+    size = 10 * (1 << 30) + 21                                   # ragged: exercises the edge warp at > 2^33
+    seed = 0xBADC0DE
+    d_n = cn.generate_device(torch.empty(size, dtype=torch.uint8, device="cuda"), 0, seed, 10)
+    d_bits = cn.encode_device(d_n)
+    nwords = cn.words_for_len(size)
+    assert d_bits.numel() == nwords
+    win = 1 << 22
+    starts = [0, (1 << 32) - win // 2, (1 << 33) - win // 2, 5 * (1 << 30) + 32 * 12345, size - win - 21]
+    for s in starts:
+        s -= s % 32
+        host = oracle.generate(min(win, size - s), seed, 10, offset=s)
+        assert np.array_equal(d_n[s : s + host.size].cpu().numpy(), host)
+        ref = oracle.encode_mt(host, "lut")
+        got = to_np_u64(d_bits[s // 32 : s // 32 + ref.size])
+        assert np.array_equal(got, ref), hex(s)
+        # (iii) the same window encoded on its own
+        alone = cn.encode_device(d_n[s : s + host.size])
+        assert _fold(alone) == _fold(d_bits[s // 32 : s // 32 + ref.size])
+    # last word: high bits beyond the 21 ragged nucleotides are zero
+    last = int(to_np_u64(d_bits[-1:])[0])
+    assert last >> (2 * (size % 32)) == 0
+    # (ii) whole-buffer round trip against the canonical form, chunked so torch temporaries stay small
+    d_out = cn.decode_device(d_bits, size)
+    lut = torch.zeros(256, dtype=torch.uint8, device="cuda")
+    for ch, canon in zip(b"ACGTUacgtu", b"ACGTTACGTT"):
+        lut[ch] = canon
+    step = 1 << 28
+    for s in range(0, size, step):
+        e = min(size, s + step)
+        assert torch.equal(d_out[s:e], lut[d_n[s:e].long()])
+    del d_out, d_n
+    # config 4: decode of arbitrary words, sampled windows vs bits_to_n_lut
+    d_w = cn.generate_words_device(torch.empty(nwords, dtype=torch.int64, device="cuda"), 0, seed + 1)
+    length = 32 * nwords - 7
+    d_dec = cn.decode_device(d_w, length)
+    for s in (0, (1 << 32) - 4096, (1 << 33) - 4096, length - (1 << 20)):
+        s -= s % 32
+        cnt = min(1 << 20, length - s)
+        words = oracle.generate_words((cnt + 31) // 32, seed + 1, first_word=s // 32)
+        assert d_dec[s : s + cnt].cpu().numpy().tobytes() == oracle.decode_mt(words, cnt, "lut").tobytes()
+    # idempotence: encode(decode(w)) == w for whole words
+    re = cn.encode_device(d_dec[: 32 * (nwords - 1)])
+    assert torch.equal(re, d_w[: nwords - 1])
