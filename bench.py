@@ -69,7 +69,7 @@ class ClockSampler(threading.Thread):
         self.index, self.period = index, period
         self.samples, self.reasons, self.power = [], set(), []
         self.max_mhz = None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -95,7 +95,7 @@ class ClockSampler(threading.Thread):
             "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80)),
         }
         get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
@@ -105,10 +105,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(self.period)
+            self._halt.wait(self.period)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         if self.ok:
             self.join(timeout=2)
 
@@ -297,7 +297,7 @@ def run_gpu(args, rank, local_rank, world):
         del full
 
     # ---- e2e: host-slice C-ABI calls with pinned host buffers, copies inside the timed region ----------
-    e2e = run_e2e(args, cn, lib, _lib, torch, np, rank, local_rank, world, barrier, dev)
+    e2e = None if args.no_e2e else run_e2e(args, cn, lib, _lib, torch, np, rank, local_rank, world, barrier, dev)
 
     # ---- CPU baseline beside it (rank 0, N == 1 only) --------------------------------------------------
     cpu = None
@@ -448,6 +448,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-assemble", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-slice leg (profiling runs only)")
     args = ap.parse_args()
 
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)

@@ -111,7 +111,6 @@ def test_host_unaligned_slices(cn, oracle, offset):
     n = base[offset:]                                            # a &[u8] can start anywhere
     assert np.array_equal(cn.n_to_bits_cuda(n), oracle.n_to_bits(n, "lut"))
     words = oracle.n_to_bits(n, "lut")
-    buf = np.empty(n.size + offset, dtype=np.uint8)
     assert cn.bits_to_n_cuda(words, n.size) == oracle.canonical(n)
 
 
@@ -138,14 +137,14 @@ def test_host_pinned_buffers(cn, oracle, torch_cuda):
     ref = oracle.n_to_bits(n, "lut")
     src = torch.from_numpy(n).pin_memory()
     out = torch.empty(ref.size, dtype=torch.int64).pin_memory()
-    dec = torch.empty(size, dtype=torch.uint8).pin_memory()
+    dec = torch.empty(size + 64, dtype=torch.uint8).pin_memory()
     for strategy in (0, 1):
         assert lib.cn_set_host_strategy(strategy, 1 << 20) == 0
         out.zero_(); dec.zero_()
         _lib.check(lib.cn_n_to_bits_host(src.data_ptr(), size, out.data_ptr()))
         assert np.array_equal(out.numpy().view(np.uint64), ref)
         _lib.check(lib.cn_bits_to_n_host(out.data_ptr(), ref.size, size, dec.data_ptr()))
-        assert dec.numpy().tobytes() == oracle.canonical(n)
+        assert dec.numpy()[:size].tobytes() == oracle.canonical(n)
         # unaligned pinned sub-slices
         _lib.check(lib.cn_n_to_bits_host(src.data_ptr() + 3, size - 3, out.data_ptr()))
         assert np.array_equal(out.numpy().view(np.uint64)[: (size - 3 + 31) // 32], oracle.n_to_bits(n[3:], "lut"))
