@@ -1,0 +1,61 @@
+// cute_nucleotides.hpp -- C++ host-side mirror of the reference module `cute_nucleotides::n_to_bits`
+// (src/n_to_bits.rs) on top of the C ABI (include/cute_nucleotides_cuda.h).
+//
+// The reference is compiled code (Rust) whose operator API is a naming family:
+//     pub fn n_to_bits_<variant>(n: &[u8]) -> Vec<u64>                  src/n_to_bits.rs:34,80,121,172,213
+//     pub fn bits_to_n_<variant>(bits: &[u64], len: usize) -> Vec<u8>   src/n_to_bits.rs:51,265,309,346
+// This header adds the `_cuda` variant with the same argument meaning, the same ownership (the callee
+// returns an owned vector that the caller's allocator frees) and the same error behaviour: where the
+// reference panics with "The length is greater than the number of nucleotides!" (:52-54) this throws
+// std::length_error carrying the same text.  Any CUDA failure throws std::runtime_error -- there is
+// no CPU fallback.  Rust cannot be compiled in this image; rust/src/lib.rs is the same shim in Rust.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <string_view>
+#include <vector>
+
+#include "../../include/cute_nucleotides_cuda.h"
+
+namespace cute_nucleotides {
+namespace n_to_bits {
+
+inline void check_status(int status)
+{
+    if (status == CN_OK) return;
+    if (status == CN_ERR_LENGTH) throw std::length_error(cn_length_panic_message());
+    throw std::runtime_error(std::string("cute_nucleotides_cuda: ") + cn_last_error());
+}
+
+/// Encode `{A, T/U, C, G}` (any case) into pairs of bits (`{00, 10, 01, 11}`) packed into 64-bit integers
+/// on the GPU.  Mirrors n_to_bits_lut (src/n_to_bits.rs:34).
+inline std::vector<uint64_t> n_to_bits_cuda(const uint8_t *n, size_t len)
+{
+    std::vector<uint64_t> res(cn_words_for_len(len));        // caller-side allocation, filled by the library
+    check_status(cn_n_to_bits_host(n, len, res.data()));
+    return res;
+}
+inline std::vector<uint64_t> n_to_bits_cuda(std::string_view n)
+{
+    return n_to_bits_cuda(reinterpret_cast<const uint8_t *>(n.data()), n.size());
+}
+inline std::vector<uint64_t> n_to_bits_cuda(const std::vector<uint8_t> &n) { return n_to_bits_cuda(n.data(), n.size()); }
+
+/// Decode pairs of bits from packed 64-bit integers to a byte string of `{A, T, C, G}` on the GPU.
+/// Mirrors bits_to_n_lut (src/n_to_bits.rs:51): throws std::length_error if len > 32 * bits.size().
+inline std::vector<uint8_t> bits_to_n_cuda(const uint64_t *bits, size_t nwords, size_t len)
+{
+    if (len > (nwords << 5)) throw std::length_error(cn_length_panic_message());
+    std::vector<uint8_t> res(len);
+    check_status(cn_bits_to_n_host(bits, nwords, len, res.data()));
+    return res;
+}
+inline std::vector<uint8_t> bits_to_n_cuda(const std::vector<uint64_t> &bits, size_t len)
+{
+    return bits_to_n_cuda(bits.data(), bits.size(), len);
+}
+
+}  // namespace n_to_bits
+}  // namespace cute_nucleotides

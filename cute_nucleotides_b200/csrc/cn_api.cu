@@ -47,7 +47,8 @@ std::atomic<uint64_t> g_launches{0};
 // tuning state (process-wide, set once by harnesses; plain loads on the hot path)
 // ------------------------------------------------------------------------------------------------
 struct Tuning { int vec, unroll, threads; };
-Tuning g_tune[2] = {{16, 4, 256}, {16, 4, 256}};
+// measured best on B200 (profiles/tune_r01.jsonl): 256-bit accesses, one vector per thread, 256 threads
+Tuning g_tune[2] = {{32, 1, 256}, {32, 1, 256}};
 int g_host_strategy = 0;
 size_t g_host_chunk = (size_t)16 << 20;      // ASCII bytes per pipeline chunk
 
@@ -126,6 +127,14 @@ cudaError_t pick_unroll(const Tuning &t, const A &a, cudaStream_t s)
 
 inline uintptr_t addr(const void *p) { return reinterpret_cast<uintptr_t>(p); }
 
+// The tuning asked for 256-bit accesses but the pointer is only 16-byte aligned: use 128-bit accesses
+// and twice the unroll so each thread keeps the same number of bytes in flight.
+inline Tuning narrow(Tuning t)
+{
+    if (t.vec == 32) { t.vec = 16; if (t.unroll < 8) t.unroll *= 2; }
+    return t;
+}
+
 int encode_device(const void *d_n, size_t len, void *d_out, cudaStream_t s)
 {
     if (len == 0) return CN_OK;
@@ -149,7 +158,7 @@ int encode_device(const void *d_n, size_t len, void *d_out, cudaStream_t s)
         } else {
             a.nvec = len >> 4;
             a.edge_first = a.nvec;
-            e = pick_unroll<true, 16>(t, a, s);
+            e = pick_unroll<true, 16>(narrow(t), a, s);
         }
     } else {
         // the body reads aligned vectors i and i+1 for group i; keep both inside [d_n, d_n + len)
@@ -186,7 +195,7 @@ int decode_device(const void *d_bits, size_t nwords, size_t len, void *d_out, cu
         } else {
             a.nvec = len >> 4;
             a.edge_from = a.nvec << 4;
-            e = pick_unroll<false, 16>(t, a, s);
+            e = pick_unroll<false, 16>(narrow(t), a, s);
         }
     } else {
         size_t head = 16 - mis;                    // nucleotides until the destination is 16-byte aligned

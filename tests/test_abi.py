@@ -41,7 +41,7 @@ def test_pure_host_entry_points(cn):
     for length in (0, 1, 31, 32, 33, 64, 65, 10 * (1 << 30), 10 * (1 << 30) + 1):
         assert lib.cn_words_for_len(length) == (length + 31) // 32 == cn.words_for_len(length)
     assert lib.cn_length_panic_message() == b"The length is greater than the number of nucleotides!"
-    assert lib.cn_set_tuning(0, 16, 4, 256) == 0
+    assert lib.cn_set_tuning(0, 32, 1, 256) == 0
     assert lib.cn_set_tuning(0, 24, 4, 256) == _lib.CN_ERR_ARG and b"unsupported" in lib.cn_last_error()
 
 

@@ -1,0 +1,148 @@
+// cn_harness.cpp -- C++ stand-in for the reference's `cargo test` / `cargo bench` on the `_cuda` variant
+// (Rust cannot be compiled in this image).  It only uses the C++ host mirror and, through it, the C ABI.
+//
+//   cn_harness test    known-answer tests written like the reference's (src/n_to_bits.rs:408-470) plus
+//                      the cases the reference leaves untested; exit code 0 = all pass
+//   cn_harness bench   the reference's criterion groups `n_to_bits` and `bits_to_n`
+//                      (benches/bench_n_to_bits.rs:9-23, 37-50): 40 000 nt of "ATCG", Throughput::Bytes(40000),
+//                      output allocation inside the timed region; also 1 MiB, 64 MiB and 1 GiB inputs
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../cute_nucleotides_b200/cpp/cute_nucleotides.hpp"
+
+using namespace cute_nucleotides::n_to_bits;
+
+static int g_failed = 0;
+#define ASSERT_EQ(a, b)                                                                        \
+    do {                                                                                       \
+        if (!((a) == (b))) { std::printf("FAILED %s:%d  %s == %s\n", __FILE__, __LINE__, #a, #b); g_failed++; } \
+    } while (0)
+
+static std::vector<uint8_t> bytes(const std::string &s) { return std::vector<uint8_t>(s.begin(), s.end()); }
+static std::string repeat(const std::string &unit, size_t times)
+{
+    std::string s;
+    s.reserve(unit.size() * times);
+    for (size_t i = 0; i < times; i++) s += unit;
+    return s;
+}
+
+static void test_n_to_bits_cuda()
+{   // src/n_to_bits.rs:412-417 (and every other encoder test)
+    ASSERT_EQ(n_to_bits_cuda("ATCGATCGATCGATCGATCGATCGATCGATCG"),
+              (std::vector<uint64_t>{0b1101100011011000110110001101100011011000110110001101100011011000ull}));
+    ASSERT_EQ(n_to_bits_cuda("ATCG"), (std::vector<uint64_t>{0b11011000ull}));
+}
+
+static void test_bits_to_n_cuda()
+{   // src/n_to_bits.rs:419-423
+    ASSERT_EQ(bits_to_n_cuda(std::vector<uint64_t>{0b1101100011011000110110001101100011011000110110001101100011011000ull}, 32),
+              bytes("ATCGATCGATCGATCGATCGATCGATCGATCG"));
+}
+
+static void test_case_insensitive_and_u()
+{   // BYTE_LUT maps a/A, c/C, g/G, t/T, u/U (src/n_to_bits.rs:8-21); decode is always upper case, U -> T
+    ASSERT_EQ(n_to_bits_cuda("atcguAUCG"), n_to_bits_cuda("ATCGTATCG"));
+    auto w = n_to_bits_cuda("acgtuACGTU");
+    ASSERT_EQ(bits_to_n_cuda(w, 10), bytes("ACGTTACGTT"));
+}
+
+static void test_body_and_tail_lengths()
+{
+    const std::string unit = "GATTACAgattacaUuCcGgAaTt";
+    for (size_t len : {0, 1, 31, 32, 33, 63, 64, 65, 127, 129, 1000, 40000, 100003}) {
+        std::string s = repeat(unit, len / unit.size() + 1).substr(0, len);
+        auto w = n_to_bits_cuda(s);
+        ASSERT_EQ(w.size(), (len + 31) / 32);
+        if (len % 32) ASSERT_EQ(w.back() >> (2 * (len % 32)), 0ull);          // unused high bits are zero
+        std::string canon = s;
+        for (auto &c : canon) { c = (char)std::toupper((unsigned char)c); if (c == 'U') c = 'T'; }
+        ASSERT_EQ(bits_to_n_cuda(w, len), bytes(canon));
+        if (len > 40) ASSERT_EQ(bits_to_n_cuda(w, len - 37), bytes(canon.substr(0, len - 37)));   // truncating len
+    }
+}
+
+static void test_length_panic()
+{   // src/n_to_bits.rs:52-54: panic!("The length is greater than the number of nucleotides!")
+    bool thrown = false;
+    try { bits_to_n_cuda(std::vector<uint64_t>{0, 0}, 65); }
+    catch (const std::length_error &e) { thrown = std::string(e.what()) == "The length is greater than the number of nucleotides!"; }
+    ASSERT_EQ(thrown, true);
+    ASSERT_EQ(bits_to_n_cuda(std::vector<uint64_t>{0, 0}, 64), bytes(std::string(64, 'A')));
+}
+
+static void test_unaligned_slice()
+{
+    std::string s = repeat("ATCGGCTA", 5000);
+    for (size_t off : {1, 3, 7, 13}) {
+        std::string_view v(s.data() + off, s.size() - off);
+        auto w = n_to_bits_cuda(v);
+        ASSERT_EQ(bits_to_n_cuda(w, v.size()), bytes(std::string(v)));
+    }
+}
+
+template <typename F> static double median_seconds(F f, int min_iters, double min_total)
+{
+    std::vector<double> t;
+    double total = 0;
+    while ((int)t.size() < min_iters || total < min_total) {
+        auto a = std::chrono::steady_clock::now();
+        f();
+        auto b = std::chrono::steady_clock::now();
+        t.push_back(std::chrono::duration<double>(b - a).count());
+        total += t.back();
+        if (t.size() > 200000) break;
+    }
+    std::sort(t.begin(), t.end());
+    return t[t.size() / 2];
+}
+
+static void bench_group(size_t repeat_count)
+{
+    const std::string n = repeat("ATCG", repeat_count);          // get_nucleotides(), benches/bench_n_to_bits.rs:68-70
+    const size_t len = n.size();
+    const auto bits = n_to_bits_cuda(n);                         // get_bits(), :76-78
+    n_to_bits_cuda(n);
+    double te = median_seconds([&] { auto r = n_to_bits_cuda(n); asm volatile("" ::"r"(r.data()) : "memory"); }, 20, 0.5);
+    double td = median_seconds([&] { auto r = bits_to_n_cuda(bits, len); asm volatile("" ::"r"(r.data()) : "memory"); }, 20, 0.5);
+    const double gib = 1024.0 * 1024.0 * 1024.0;
+    std::printf("{\"group\": \"n_to_bits\", \"function\": \"n_to_bits_cuda\", \"nucleotides\": %zu, \"time_us\": %.2f, \"thrpt_gib_s\": %.4f}\n",
+                len, te * 1e6, len / te / gib);
+    std::printf("{\"group\": \"bits_to_n\", \"function\": \"bits_to_n_cuda\", \"nucleotides\": %zu, \"time_us\": %.2f, \"thrpt_gib_s\": %.4f}\n",
+                len, td * 1e6, len / td / gib);
+    std::fflush(stdout);
+}
+
+int main(int argc, char **argv)
+{
+    const std::string mode = argc > 1 ? argv[1] : "test";
+    try {
+        if (mode == "test") {
+            test_n_to_bits_cuda();
+            test_bits_to_n_cuda();
+            test_case_insensitive_and_u();
+            test_body_and_tail_lengths();
+            test_length_panic();
+            test_unaligned_slice();
+            std::printf(g_failed ? "test result: FAILED. %d failed\n" : "test result: ok. 6 passed; %d failed\n", g_failed);
+            return g_failed ? 1 : 0;
+        }
+        if (mode == "bench") {
+            bench_group(10000);                 // the reference's bench size: 40 000 nt
+            bench_group((1u << 20) / 4);        // 1 MiB
+            bench_group((64u << 20) / 4);       // 64 MiB
+            bench_group((1u << 30) / 4);        // 1 GiB
+            return 0;
+        }
+    } catch (const std::exception &e) {
+        std::printf("error: %s\n", e.what());
+        return 2;
+    }
+    std::printf("usage: cn_harness test|bench\n");
+    return 64;
+}
