@@ -1,0 +1,100 @@
+"""Multi-GPU host logic: shard one logical sequence by offset, one process per GPU (torch.distributed).
+
+The codec needs no exchange: packed word w depends only on nucleotides 32w..32w+31 (src/n_to_bits.rs:39-42),
+so rank r encodes / decodes its own contiguous range and NO collective sits on the data path.  The only
+collective the path can use is assembling the packed shards afterwards (`assemble_packed`, an all-gather);
+bench.py times it separately.  This module is backend-agnostic (nccl on GPUs, gloo in the CPU tests): it
+only plans ranges and moves already-encoded tensors, it never computes codes itself.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+GRANULE = 32          # nucleotides per packed u64: shard boundaries must be multiples of this
+
+
+def shard_bounds(total_len: int, world: int, rank: int, granule: int = GRANULE) -> Tuple[int, int]:
+    """Contiguous range [start, end) of nucleotides owned by `rank`.
+
+    Boundaries are multiples of `granule` (itself a multiple of 32) so every rank writes whole, aligned words;
+    ranges are balanced to within one granule; the ragged global tail (total_len % 32) lands on the last
+    non-empty rank.  Ranks beyond the data get an empty range."""
+    if granule % GRANULE:
+        raise ValueError("granule must be a multiple of 32 nucleotides")
+    if not 0 <= rank < world:
+        raise ValueError("rank out of range")
+    units = -(-total_len // granule)                       # ceil
+    base, extra = divmod(units, world)
+    first = rank * base + min(rank, extra)
+    count = base + (1 if rank < extra else 0)
+    start = min(first * granule, total_len)
+    end = min((first + count) * granule, total_len)
+    return start, end
+
+
+def all_bounds(total_len: int, world: int, granule: int = GRANULE) -> List[Tuple[int, int]]:
+    return [shard_bounds(total_len, world, r, granule) for r in range(world)]
+
+
+def words_for_len(length: int) -> int:
+    return (length >> 5) + (1 if length & 31 else 0)
+
+
+def word_bounds(total_len: int, world: int, rank: int, granule: int = GRANULE) -> Tuple[int, int]:
+    """Range of packed words produced by `rank` (start is exact because shard starts are multiples of 32)."""
+    start, end = shard_bounds(total_len, world, rank, granule)
+    return start >> 5, (start >> 5) + words_for_len(end - start)
+
+
+def assemble_packed(local_words, total_len: int, group=None, granule: int = GRANULE):
+    """All-gather the packed shards: every rank returns the full ceil(total_len/32)-word tensor.
+
+    `local_words` is this rank's 8-byte-element tensor (CPU for gloo, CUDA for nccl) holding exactly the words
+    of its shard.  Equal shards use all_gather_into_tensor (one NCCL collective, in place); ragged shards fall
+    back to all_gather on padded buffers."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    spans = [word_bounds(total_len, world, r, granule) for r in range(world)]
+    counts = [e - s for s, e in spans]
+    if local_words.numel() != counts[rank]:
+        raise ValueError(f"rank {rank}: expected {counts[rank]} words, got {local_words.numel()}")
+    total_words = words_for_len(total_len)
+    full = torch.empty(total_words, dtype=local_words.dtype, device=local_words.device)
+    if len(set(counts)) == 1 and counts[0] * world == total_words:
+        dist.all_gather_into_tensor(full, local_words.contiguous(), group=group)
+        return full
+    width = max(counts)
+    padded = torch.zeros(width, dtype=local_words.dtype, device=local_words.device)
+    padded[: counts[rank]] = local_words
+    pieces = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(pieces, padded, group=group)
+    for (s, e), piece in zip(spans, pieces):
+        full[s:e] = piece[: e - s]
+    return full
+
+
+def encode_sharded(n_shard, total_len: int, group=None, assemble: bool = False, granule: int = GRANULE):
+    """Encode this rank's shard on its GPU (cn_encode_device through the C ABI); optionally assemble."""
+    import torch.distributed as dist
+    from . import n_to_bits
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    start, end = shard_bounds(total_len, world, rank, granule)
+    if n_shard.numel() != end - start:
+        raise ValueError(f"rank {rank}: shard must hold nucleotides [{start}, {end})")
+    words = n_to_bits.encode_device(n_shard)
+    return assemble_packed(words, total_len, group, granule) if assemble else words
+
+
+def decode_sharded(full_words, total_len: int, group=None, granule: int = GRANULE):
+    """Decode this rank's range of a packed tensor every rank already holds (e.g. after assemble/broadcast)."""
+    import torch.distributed as dist
+    from . import n_to_bits
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    start, end = shard_bounds(total_len, world, rank, granule)
+    ws, we = word_bounds(total_len, world, rank, granule)
+    return n_to_bits.decode_device(full_words[ws:we], end - start)
