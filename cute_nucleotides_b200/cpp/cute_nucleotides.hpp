@@ -12,6 +12,8 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <memory>
+#include <new>
 #include <stdexcept>
 #include <string>
 #include <string_view>
@@ -22,6 +24,16 @@
 namespace cute_nucleotides {
 namespace n_to_bits {
 
+// Rust's Vec::with_capacity + set_len does not zero the buffer the library is about to overwrite;
+// std::vector(n) would.  This allocator default-initialises instead, so the mirrors cost the same.
+template <class T> struct default_init_allocator : std::allocator<T> {
+    template <class U> struct rebind { using other = default_init_allocator<U>; };
+    template <class U> void construct(U *p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new (static_cast<void *>(p)) U; }
+    template <class U, class... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
+};
+using Words = std::vector<uint64_t, default_init_allocator<uint64_t>>;   // the Vec<u64> of the reference
+using Bytes = std::vector<uint8_t, default_init_allocator<uint8_t>>;     // the Vec<u8> of the reference
+
 inline void check_status(int status)
 {
     if (status == CN_OK) return;
@@ -31,28 +43,28 @@ inline void check_status(int status)
 
 /// Encode `{A, T/U, C, G}` (any case) into pairs of bits (`{00, 10, 01, 11}`) packed into 64-bit integers
 /// on the GPU.  Mirrors n_to_bits_lut (src/n_to_bits.rs:34).
-inline std::vector<uint64_t> n_to_bits_cuda(const uint8_t *n, size_t len)
+inline Words n_to_bits_cuda(const uint8_t *n, size_t len)
 {
-    std::vector<uint64_t> res(cn_words_for_len(len));        // caller-side allocation, filled by the library
+    Words res(cn_words_for_len(len));                        // caller-side allocation, filled by the library
     check_status(cn_n_to_bits_host(n, len, res.data()));
     return res;
 }
-inline std::vector<uint64_t> n_to_bits_cuda(std::string_view n)
+inline Words n_to_bits_cuda(std::string_view n)
 {
     return n_to_bits_cuda(reinterpret_cast<const uint8_t *>(n.data()), n.size());
 }
-inline std::vector<uint64_t> n_to_bits_cuda(const std::vector<uint8_t> &n) { return n_to_bits_cuda(n.data(), n.size()); }
+inline Words n_to_bits_cuda(const std::vector<uint8_t> &n) { return n_to_bits_cuda(n.data(), n.size()); }
 
 /// Decode pairs of bits from packed 64-bit integers to a byte string of `{A, T, C, G}` on the GPU.
 /// Mirrors bits_to_n_lut (src/n_to_bits.rs:51): throws std::length_error if len > 32 * bits.size().
-inline std::vector<uint8_t> bits_to_n_cuda(const uint64_t *bits, size_t nwords, size_t len)
+inline Bytes bits_to_n_cuda(const uint64_t *bits, size_t nwords, size_t len)
 {
     if (len > (nwords << 5)) throw std::length_error(cn_length_panic_message());
-    std::vector<uint8_t> res(len);
+    Bytes res(len);
     check_status(cn_bits_to_n_host(bits, nwords, len, res.data()));
     return res;
 }
-inline std::vector<uint8_t> bits_to_n_cuda(const std::vector<uint64_t> &bits, size_t len)
+template <class A> inline Bytes bits_to_n_cuda(const std::vector<uint64_t, A> &bits, size_t len)
 {
     return bits_to_n_cuda(bits.data(), bits.size(), len);
 }

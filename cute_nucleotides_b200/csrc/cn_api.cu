@@ -12,10 +12,16 @@
 #include "codec_kernels.cuh"
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <mutex>
+#include <thread>
+#include <vector>
+#include <sys/mman.h>
 
 namespace {
 
@@ -51,6 +57,7 @@ struct Tuning { int vec, unroll, threads; };
 Tuning g_tune[2] = {{32, 1, 256}, {32, 1, 256}};
 int g_host_strategy = 0;
 size_t g_host_chunk = (size_t)16 << 20;      // ASCII bytes per pipeline chunk
+size_t g_host_small = (size_t)256 << 10;     // nucleotides at or below which the single-launch path is used
 
 bool tuning_ok(int vec, int unroll, int threads)
 {
@@ -212,6 +219,89 @@ int decode_device(const void *d_bits, size_t nwords, size_t len, void *d_out, cu
 }
 
 // ------------------------------------------------------------------------------------------------
+// staging copier.  Pageable caller memory cannot be DMA'd, so it is copied through pinned staging;
+// one thread moves ~10 GB/s (less into never-touched pages), PCIe Gen5 moves > 50 GB/s, so large
+// copies are cut into slices executed by a small process-wide pool (CN_HOST_THREADS, default
+// min(8, cores/2)) with the calling thread taking a slice too.  The pool is created on first use and
+// intentionally never destroyed (its threads only ever wait on a condition variable).
+// ------------------------------------------------------------------------------------------------
+class CopyPool {
+public:
+    static CopyPool &get()
+    {
+        static CopyPool *pool = new CopyPool();      // leaked on purpose: no join at process exit
+        return *pool;
+    }
+
+    void copy(void *dst, const void *src, size_t bytes)
+    {
+        constexpr size_t kMinSlice = (size_t)256 << 10;
+        size_t parts = bytes / kMinSlice;
+        if (parts > threads_.size() + 1) parts = threads_.size() + 1;
+        if (parts <= 1) { memcpy(dst, src, bytes); return; }
+        const size_t slice = ((bytes / parts) + 4095) & ~(size_t)4095;
+        Job job;
+        size_t off = slice;                            // slice 0 is the caller's
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            while (off < bytes) {
+                size_t n = bytes - off < slice ? bytes - off : slice;
+                queue_.push_back(Task{static_cast<uint8_t *>(dst) + off, static_cast<const uint8_t *>(src) + off, n, &job});
+                job.pending++;
+                off += n;
+            }
+        }
+        cv_.notify_all();
+        memcpy(dst, src, slice < bytes ? slice : bytes);
+        std::unique_lock<std::mutex> lk(mu_);
+        job.done_cv.wait(lk, [&] { return job.pending == 0; });
+    }
+
+private:
+    struct Job { int pending = 0; std::condition_variable done_cv; };
+    struct Task { uint8_t *dst; const uint8_t *src; size_t bytes; Job *job; };
+
+    CopyPool()
+    {
+        int n = 0;
+        if (const char *env = std::getenv("CN_HOST_THREADS")) n = std::atoi(env) - 1;
+        else {
+            unsigned hc = std::thread::hardware_concurrency();
+            n = (int)(hc / 2 > 8 ? 8 : hc / 2) - 1;
+        }
+        if (n < 0) n = 0;
+        if (n > 63) n = 63;
+        for (int i = 0; i < n; i++) {
+            threads_.emplace_back([this] { run(); });
+            threads_.back().detach();
+        }
+    }
+    void run()
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        for (;;) {
+            cv_.wait(lk, [&] { return !queue_.empty(); });
+            Task t = queue_.front();
+            queue_.pop_front();
+            lk.unlock();
+            memcpy(t.dst, t.src, t.bytes);
+            lk.lock();
+            if (--t.job->pending == 0) t.job->done_cv.notify_all();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<Task> queue_;
+    std::vector<std::thread> threads_;
+};
+
+inline void staged_copy(void *dst, const void *src, size_t bytes)
+{
+    if (bytes < ((size_t)512 << 10)) memcpy(dst, src, bytes);
+    else CopyPool::get().copy(dst, src, bytes);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-slice pipeline.  Per calling thread: kSlots slots, each with its own stream, a pinned and a
 // device staging buffer per direction.  Chunk c uses slot c % kSlots, so while chunk c's H2D copy
 // runs, chunk c-1's kernel and chunk c-2's D2H copy run on other streams/copy engines.
@@ -301,6 +391,22 @@ int host_codec(bool encode, const uint8_t *src, uint8_t *dst, size_t len, size_t
 
     const size_t src_bytes = encode ? len : nwords * 8;
     const size_t dst_bytes = encode ? cn_words_for_len(len) * 8 : len;
+
+    // Small inputs (the reference's own bench is 40 000 nt) are latency-bound: skip the pointer queries and
+    // the copy engines, stage through slot 0's pinned buffers and let ONE kernel read and write them in place
+    // over PCIe -- a single launch and a single synchronisation.
+    if (len <= g_host_small && len <= p.chunk) {
+        Slot &sl = p.slot[0];
+        uint8_t *pin_in = encode ? sl.pin_big : sl.pin_small;
+        uint8_t *pin_out = encode ? sl.pin_small : sl.pin_big;
+        memcpy(pin_in, src, src_bytes);
+        rc = encode ? encode_device(pin_in, len, pin_out, sl.stream) : decode_device(pin_in, nwords, len, pin_out, sl.stream);
+        if (rc != CN_OK) return rc;
+        CN_CUDA(cudaStreamSynchronize(sl.stream));
+        memcpy(dst, pin_out, dst_bytes);
+        return CN_OK;
+    }
+
     const bool src_pinned = is_pinned(src, src_bytes);
     const bool dst_pinned = is_pinned(dst, dst_bytes);
     const bool zero_copy = g_host_strategy == 1;
@@ -314,7 +420,20 @@ int host_codec(bool encode, const uint8_t *src, uint8_t *dst, size_t len, size_t
         return CN_OK;
     }
 
-    const size_t chunk = p.chunk;                       // nucleotides per chunk, multiple of 32
+    // Nucleotides per chunk (multiple of 4096).  Mid-sized inputs are cut into ~8 chunks so that staging
+    // copies, both DMA directions and the kernel overlap; large inputs use the full staging size.
+    size_t chunk = p.chunk;
+    if (len / 8 < chunk) {
+        size_t c8 = ((len / 8) + 4095) & ~(size_t)4095;
+        const size_t floor_nt = (size_t)1 << 20;
+        chunk = c8 < floor_nt ? (floor_nt < p.chunk ? floor_nt : p.chunk) : c8;
+    }
+    // A large pageable destination is usually a freshly allocated Vec: ask for transparent huge pages so the
+    // first-touch faults taken while copying the result out are per 2 MiB, not per 4 KiB (hint only).
+    if (!dst_pinned && dst_bytes >= ((size_t)8 << 20)) {
+        const uintptr_t lo = (addr(dst) + 0x1FFFFF) & ~(uintptr_t)0x1FFFFF, hi = (addr(dst) + dst_bytes) & ~(uintptr_t)0x1FFFFF;
+        if (hi > lo) (void)madvise(reinterpret_cast<void *>(lo), hi - lo, MADV_HUGEPAGE);
+    }
     size_t done_nt = 0;
     int c = 0;
     int first_error = CN_OK;
@@ -323,7 +442,7 @@ int host_codec(bool encode, const uint8_t *src, uint8_t *dst, size_t len, size_t
         // retire whatever this slot was doing kSlots chunks ago
         if (sl.busy) {
             CN_CUDA(cudaEventSynchronize(sl.done));
-            if (sl.dst_bytes) memcpy(dst + sl.dst_off, encode ? sl.pin_small : sl.pin_big, sl.dst_bytes);
+            if (sl.dst_bytes) staged_copy(dst + sl.dst_off, encode ? sl.pin_small : sl.pin_big, sl.dst_bytes);
             sl.busy = false;
         }
         const size_t nt = (len - done_nt < chunk) ? len - done_nt : chunk;
@@ -338,7 +457,7 @@ int host_codec(bool encode, const uint8_t *src, uint8_t *dst, size_t len, size_t
         uint8_t *dev_out = encode ? sl.dev_small : sl.dev_big;
 
         const uint8_t *h_in = src + in_off;
-        if (!src_pinned) { memcpy(pin_in, h_in, in_bytes); h_in = pin_in; }
+        if (!src_pinned) { staged_copy(pin_in, h_in, in_bytes); h_in = pin_in; }
         uint8_t *h_out = dst_pinned ? dst + out_off : pin_out;
 
         if (zero_copy) {
@@ -364,7 +483,7 @@ int host_codec(bool encode, const uint8_t *src, uint8_t *dst, size_t len, size_t
         cudaError_t e = cudaEventSynchronize(sl.done);
         if (e != cudaSuccess && first_error == CN_OK)
             first_error = fail(CN_ERR_CUDA, "host pipeline drain failed: %s", cudaGetErrorString(e));
-        if (e == cudaSuccess && sl.dst_bytes) memcpy(dst + sl.dst_off, encode ? sl.pin_small : sl.pin_big, sl.dst_bytes);
+        if (e == cudaSuccess && sl.dst_bytes) staged_copy(dst + sl.dst_off, encode ? sl.pin_small : sl.pin_big, sl.dst_bytes);
         sl.busy = false;
     }
     return first_error;

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../cute_nucleotides_b200/cpp/cute_nucleotides.hpp"
@@ -18,9 +19,14 @@
 using namespace cute_nucleotides::n_to_bits;
 
 static int g_failed = 0;
+template <class A, class B> static bool same(const A &a, const B &b)
+{
+    if constexpr (std::is_arithmetic<A>::value) return a == b;
+    else return a.size() == b.size() && std::equal(a.begin(), a.end(), b.begin());
+}
 #define ASSERT_EQ(a, b)                                                                        \
     do {                                                                                       \
-        if (!((a) == (b))) { std::printf("FAILED %s:%d  %s == %s\n", __FILE__, __LINE__, #a, #b); g_failed++; } \
+        if (!same((a), (b))) { std::printf("FAILED %s:%d  %s == %s\n", __FILE__, __LINE__, #a, #b); g_failed++; } \
     } while (0)
 
 static std::vector<uint8_t> bytes(const std::string &s) { return std::vector<uint8_t>(s.begin(), s.end()); }
