@@ -7,5 +7,8 @@ from .n_to_bits import (  # noqa: F401
     LengthError, bits_to_n_cuda, decode_device, encode_device, generate_device, generate_words_device,
     n_to_bits_cuda, words_for_len,
 )
+from .n_to_bits2 import (  # noqa: F401
+    bits_to_n2_cuda, decode2_device, encode2_device, generate2_device, n_to_bits2_cuda, words2_for_len,
+)
 
 __version__ = "0.1.0"

@@ -10,6 +10,7 @@
 // CN_ERR_CUDA.
 #include "../../include/cute_nucleotides_cuda.h"
 #include "codec_kernels.cuh"
+#include "codec5_kernels.cuh"
 
 #include <atomic>
 #include <condition_variable>
@@ -218,6 +219,68 @@ int decode_device(const void *d_bits, size_t nwords, size_t len, void *d_out, cu
     return CN_OK;
 }
 
+// ---- base-5 codec (src/n_to_bits2.rs) ----------------------------------------------------------------
+inline size_t words2_for_len(size_t len) { return len / 27 + ((len % 27) ? 1 : 0); }
+
+int encode2_device(const void *d_n, size_t len, void *d_out, cudaStream_t s)
+{
+    if (len == 0) return CN_OK;
+    if (!d_n || !d_out) return fail(CN_ERR_ARG, "cn_encode2_device: null pointer");
+    if (addr(d_out) & 7) return fail(CN_ERR_ARG, "cn_encode2_device: output must be 8-byte aligned");
+    const size_t total = words2_for_len(len);
+    const uint8_t *in = static_cast<const uint8_t *>(d_n);
+    uint64_t *out = static_cast<uint64_t *>(d_out);
+    if ((addr(d_n) & 15) == 0) {
+        const size_t ntiles = (len / 27) / cn::kB5WarpWords;                 // tiles of complete words
+        const size_t blocks = (ntiles + 1 + cn::kB5Warps - 1) / cn::kB5Warps;
+        if (blocks > kMaxGrid) return fail(CN_ERR_ARG, "cn_encode2_device: input too large for one launch");
+        cn::b5_encode_kernel<<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(in, out, len, ntiles, total);
+    } else {
+        size_t blocks = (total + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        cn::b5_encode_scalar_kernel<<<(unsigned)blocks, 256, 0, s>>>(in, out, len, total);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(CN_ERR_CUDA, "base-5 encode kernel launch failed: %s", cudaGetErrorString(e));
+    return CN_OK;
+}
+
+int decode2_device(const void *d_bits, size_t nwords, size_t len, void *d_out, cudaStream_t s)
+{
+    if (nwords > (~(size_t)0) / 27 || len > nwords * 27) return fail(CN_ERR_LENGTH, "%s", kPanicText);   // n_to_bits2.rs:79-81
+    if (len == 0) return CN_OK;
+    if (!d_bits || !d_out) return fail(CN_ERR_ARG, "cn_decode2_device: null pointer");
+    if (addr(d_bits) & 7) return fail(CN_ERR_ARG, "cn_decode2_device: packed input must be 8-byte aligned");
+    const size_t total = words2_for_len(len);
+    const uint64_t *bits = static_cast<const uint64_t *>(d_bits);
+    uint8_t *out = static_cast<uint8_t *>(d_out);
+    if ((addr(d_out) & 15) == 0) {
+        const size_t ntiles = (len / 27) / cn::kB5WarpWords;
+        const size_t blocks = (ntiles + 1 + cn::kB5Warps - 1) / cn::kB5Warps;
+        if (blocks > kMaxGrid) return fail(CN_ERR_ARG, "cn_decode2_device: input too large for one launch");
+        cn::b5_decode_kernel<<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(bits, out, len, ntiles, total);
+    } else {
+        size_t blocks = (total + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        cn::b5_decode_scalar_kernel<<<(unsigned)blocks, 256, 0, s>>>(bits, out, len, total);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(CN_ERR_CUDA, "base-5 decode kernel launch failed: %s", cudaGetErrorString(e));
+    return CN_OK;
+}
+
+// What the host pipeline needs to know about a codec: nucleotides per word and the device entry points.
+struct Codec {
+    unsigned group;                                                        // 32 (2-bit) or 27 (base-5)
+    int (*enc)(const void *, size_t, void *, cudaStream_t);
+    int (*dec)(const void *, size_t, size_t, void *, cudaStream_t);
+    size_t words(size_t nt) const { return nt / group + ((nt % group) ? 1 : 0); }
+};
+const Codec kCodec2bit{32, encode_device, decode_device};
+const Codec kCodecBase5{27, encode2_device, decode2_device};
+
 // ------------------------------------------------------------------------------------------------
 // staging copier.  Pageable caller memory cannot be DMA'd, so it is copied through pinned staging;
 // one thread moves ~10 GB/s (less into never-touched pages), PCIe Gen5 moves > 50 GB/s, so large
@@ -380,27 +443,31 @@ bool is_pinned(const void *p, size_t bytes)
     return a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost;
 }
 
-// One implementation for both directions: `big` is the ASCII side, `small` the packed side.
+// One implementation for both directions and both codecs: `big` is the ASCII side, `small` the packed side.
 //   encode: src = ASCII (len bytes)          dst = packed (8*words bytes)
 //   decode: src = packed (8*nwords bytes)    dst = ASCII (len bytes)
-int host_codec(bool encode, const uint8_t *src, uint8_t *dst, size_t len, size_t nwords)
+int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, size_t len)
 {
     HostPipe &p = t_pipe;
     int rc = pipe_prepare(p);
     if (rc != CN_OK) return rc;
 
+    const size_t nwords = cd.words(len);
     const size_t src_bytes = encode ? len : nwords * 8;
-    const size_t dst_bytes = encode ? cn_words_for_len(len) * 8 : len;
+    const size_t dst_bytes = encode ? nwords * 8 : len;
+    // Staging holds p.chunk ASCII bytes and p.chunk/4 (+64) packed bytes per slot; the base-5 codec packs
+    // 8 bytes per 27 nucleotides (> 1/4), so its chunks are 3/4 of the staging size.
+    const size_t max_nt = cd.group == 32 ? p.chunk : p.chunk / 4 * 3;
 
     // Small inputs (the reference's own bench is 40 000 nt) are latency-bound: skip the pointer queries and
     // the copy engines, stage through slot 0's pinned buffers and let ONE kernel read and write them in place
     // over PCIe -- a single launch and a single synchronisation.
-    if (len <= g_host_small && len <= p.chunk) {
+    if (len <= g_host_small && len <= max_nt) {
         Slot &sl = p.slot[0];
         uint8_t *pin_in = encode ? sl.pin_big : sl.pin_small;
         uint8_t *pin_out = encode ? sl.pin_small : sl.pin_big;
         memcpy(pin_in, src, src_bytes);
-        rc = encode ? encode_device(pin_in, len, pin_out, sl.stream) : decode_device(pin_in, nwords, len, pin_out, sl.stream);
+        rc = encode ? cd.enc(pin_in, len, pin_out, sl.stream) : cd.dec(pin_in, nwords, len, pin_out, sl.stream);
         if (rc != CN_OK) return rc;
         CN_CUDA(cudaStreamSynchronize(sl.stream));
         memcpy(dst, pin_out, dst_bytes);
@@ -414,19 +481,23 @@ int host_codec(bool encode, const uint8_t *src, uint8_t *dst, size_t len, size_t
     // zero-copy with both sides page-locked: a single kernel streams over PCIe in both directions
     if (zero_copy && src_pinned && dst_pinned) {
         cudaStream_t s = p.slot[0].stream;
-        rc = encode ? encode_device(src, len, dst, s) : decode_device(src, nwords, len, dst, s);
+        rc = encode ? cd.enc(src, len, dst, s) : cd.dec(src, nwords, len, dst, s);
         if (rc != CN_OK) return rc;
         CN_CUDA(cudaStreamSynchronize(s));
         return CN_OK;
     }
 
-    // Nucleotides per chunk (multiple of 4096).  Mid-sized inputs are cut into ~8 chunks so that staging
-    // copies, both DMA directions and the kernel overlap; large inputs use the full staging size.
-    size_t chunk = p.chunk;
+    // Nucleotides per chunk: a multiple of `unit` (whole words, and whole warp tiles / 16-byte vectors where the
+    // staging size allows).  Mid-sized inputs are cut into ~8 chunks so that staging copies, both DMA directions
+    // and the kernel overlap; large inputs use the full staging size.
+    size_t unit = cd.group == 32 ? 4096 : (size_t)cn::kB5WarpBytes;
+    if (max_nt < unit) unit = cd.group;
+    size_t chunk = max_nt / unit * unit;
     if (len / 8 < chunk) {
-        size_t c8 = ((len / 8) + 4095) & ~(size_t)4095;
-        const size_t floor_nt = (size_t)1 << 20;
-        chunk = c8 < floor_nt ? (floor_nt < p.chunk ? floor_nt : p.chunk) : c8;
+        size_t c8 = (len / 8 + unit - 1) / unit * unit;
+        size_t floor_nt = ((size_t)1 << 20) / unit * unit;
+        if (floor_nt == 0 || floor_nt > chunk) floor_nt = chunk;
+        chunk = c8 < floor_nt ? floor_nt : (c8 < chunk ? c8 : chunk);
     }
     // A large pageable destination is usually a freshly allocated Vec: ask for transparent huge pages so the
     // first-touch faults taken while copying the result out are per 2 MiB, not per 4 KiB (hint only).
@@ -446,10 +517,11 @@ int host_codec(bool encode, const uint8_t *src, uint8_t *dst, size_t len, size_t
             sl.busy = false;
         }
         const size_t nt = (len - done_nt < chunk) ? len - done_nt : chunk;
-        const size_t words = cn_words_for_len(nt);
-        const size_t in_off = encode ? done_nt : (done_nt >> 5) * 8;
+        const size_t words = cd.words(nt);
+        const size_t word_off = done_nt / cd.group * 8;             // done_nt is a multiple of the group size
+        const size_t in_off = encode ? done_nt : word_off;
         const size_t in_bytes = encode ? nt : words * 8;
-        const size_t out_off = encode ? (done_nt >> 5) * 8 : done_nt;
+        const size_t out_off = encode ? word_off : done_nt;
         const size_t out_bytes = encode ? words * 8 : nt;
         uint8_t *pin_in = encode ? sl.pin_big : sl.pin_small;
         uint8_t *pin_out = encode ? sl.pin_small : sl.pin_big;
@@ -462,10 +534,10 @@ int host_codec(bool encode, const uint8_t *src, uint8_t *dst, size_t len, size_t
 
         if (zero_copy) {
             // kernel dereferences the pinned staging (or the caller's pinned side) directly
-            rc = encode ? encode_device(h_in, nt, h_out, sl.stream) : decode_device(h_in, words, nt, h_out, sl.stream);
+            rc = encode ? cd.enc(h_in, nt, h_out, sl.stream) : cd.dec(h_in, words, nt, h_out, sl.stream);
         } else {
             CN_CUDA(cudaMemcpyAsync(dev_in, h_in, in_bytes, cudaMemcpyHostToDevice, sl.stream));
-            rc = encode ? encode_device(dev_in, nt, dev_out, sl.stream) : decode_device(dev_in, words, nt, dev_out, sl.stream);
+            rc = encode ? cd.enc(dev_in, nt, dev_out, sl.stream) : cd.dec(dev_in, words, nt, dev_out, sl.stream);
             if (rc == CN_OK) CN_CUDA(cudaMemcpyAsync(h_out, dev_out, out_bytes, cudaMemcpyDeviceToHost, sl.stream));
         }
         if (rc != CN_OK) { first_error = rc; break; }
@@ -541,7 +613,7 @@ int cn_n_to_bits_host(const uint8_t *n, size_t len, uint64_t *out)
 {
     if (len == 0) return CN_OK;                                 // reference: zero-size alloc; here: nothing to do
     if (!n || !out) return fail(CN_ERR_ARG, "cn_n_to_bits_host: null pointer");
-    return host_codec(true, n, reinterpret_cast<uint8_t *>(out), len, 0);
+    return host_codec(kCodec2bit, true, n, reinterpret_cast<uint8_t *>(out), len);
 }
 
 int cn_bits_to_n_host(const uint64_t *bits, size_t nwords, size_t len, uint8_t *out)
@@ -549,7 +621,7 @@ int cn_bits_to_n_host(const uint64_t *bits, size_t nwords, size_t len, uint8_t *
     if (len > (nwords << 5) || (nwords >> 59) != 0) return fail(CN_ERR_LENGTH, "%s", kPanicText);
     if (len == 0) return CN_OK;
     if (!bits || !out) return fail(CN_ERR_ARG, "cn_bits_to_n_host: null pointer");
-    return host_codec(false, reinterpret_cast<const uint8_t *>(bits), out, len, cn_words_for_len(len));
+    return host_codec(kCodec2bit, false, reinterpret_cast<const uint8_t *>(bits), out, len);
 }
 
 int cn_encode_device(const void *d_n, size_t len, void *d_out, void *stream)
@@ -560,6 +632,46 @@ int cn_encode_device(const void *d_n, size_t len, void *d_out, void *stream)
 int cn_decode_device(const void *d_bits, size_t nwords, size_t len, void *d_out, void *stream)
 {
     return decode_device(d_bits, nwords, len, d_out, static_cast<cudaStream_t>(stream));
+}
+
+size_t cn_words2_for_len(size_t len) { return words2_for_len(len); }
+
+int cn_n_to_bits2_host(const uint8_t *n, size_t len, uint64_t *out)
+{
+    if (len == 0) return CN_OK;
+    if (!n || !out) return fail(CN_ERR_ARG, "cn_n_to_bits2_host: null pointer");
+    return host_codec(kCodecBase5, true, n, reinterpret_cast<uint8_t *>(out), len);
+}
+
+int cn_bits_to_n2_host(const uint64_t *bits, size_t nwords, size_t len, uint8_t *out)
+{
+    if (nwords > (~(size_t)0) / 27 || len > nwords * 27) return fail(CN_ERR_LENGTH, "%s", kPanicText);
+    if (len == 0) return CN_OK;
+    if (!bits || !out) return fail(CN_ERR_ARG, "cn_bits_to_n2_host: null pointer");
+    return host_codec(kCodecBase5, false, reinterpret_cast<const uint8_t *>(bits), out, len);
+}
+
+int cn_encode2_device(const void *d_n, size_t len, void *d_out, void *stream)
+{
+    return encode2_device(d_n, len, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int cn_decode2_device(const void *d_bits, size_t nwords, size_t len, void *d_out, void *stream)
+{
+    return decode2_device(d_bits, nwords, len, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int cn_generate2_device(void *d_out, size_t offset, size_t len, uint64_t seed, int alphabet, void *stream)
+{
+    if (alphabet != 5 && alphabet != 12) return fail(CN_ERR_ARG, "cn_generate2_device: alphabet must be 5 or 12");
+    if (len == 0) return CN_OK;
+    if (!d_out) return fail(CN_ERR_ARG, "cn_generate2_device: null pointer");
+    size_t blocks = (len + 255) / 256;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    cn::b5_generate_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<uint8_t *>(d_out), offset, len, seed, alphabet);
+    CN_CUDA(cudaGetLastError());
+    return CN_OK;
 }
 
 int cn_generate_device(void *d_out, size_t offset, size_t len, uint64_t seed, int alphabet, void *stream)

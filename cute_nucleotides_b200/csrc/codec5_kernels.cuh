@@ -1,0 +1,257 @@
+// codec5_kernels.cuh -- sm_100a kernels for cute-nucleotides' base-5 codec (src/n_to_bits2.rs):
+// {A, C, T/U, G, N} -> digits 0..4, three digits -> 7 bits (a + 5b + 25c), nine triplets = 27 nucleotides
+// per u64 (bit 63 unused).  Contract = n_to_bits2_lut / bits_to_n2_lut (src/n_to_bits2.rs:37-107).
+//
+// Shape of the problem on a GPU: 27 ASCII bytes <-> 8 packed bytes (1.296 B of HBM traffic per
+// nucleotide), and 27-byte groups are not aligned to anything -- but 32 groups are 864 bytes = 54 x 16 B.
+// So a WARP owns a tile of 4 x 32 words (3456 ASCII bytes, 16-byte aligned): global memory is touched only
+// with coalesced 128-bit accesses, the tile is staged in a warp-private slice of shared memory (only
+// __syncwarp, no block barrier), and each lane converts whole words out of / into shared memory.
+//
+//   encode, per lane and word: 8 LDS.32 + funnel shifts realign the lane's 27 bytes; digits come from a
+//     PRMT lookup on the low 3 ASCII bits (exactly the reference's pshufb LUT, src/n_to_bits2.rs:127-136:
+//     'A'&7=1 'C'&7=3 'T'&7=4 'U'&7=5 'N'&7=6 'G'&7=7, case-insensitive for free); a triplet sitting in
+//     bytes 0..2 (or 1..3) of a register is ONE multiply: x * (1<<16 | 5<<8 | 25) leaves a+5b+25c in
+//     byte 2 (byte 3) with no carries -- the GPU analogue of maddubs(5,25)+add (:160-163).
+//   decode, per lane and word: q = e*205>>10 (= e/5), c = e*41>>10 (= e/25), and the three digits as PRMT
+//     selector nibbles are e + 11q + 176c; PRMT against 'A','C','T','G','N' emits the letters (the
+//     reciprocal-multiply idea of :209-211,241-247 on 32-bit registers); a lane's 27 bytes are merged with
+//     its neighbour's first bytes by one warp shuffle so shared memory is written in whole words.
+#pragma once
+#include "codec_kernels.cuh"
+
+namespace cn {
+
+constexpr int kB5Nt = 27;                       // nucleotides per word
+constexpr int kB5WarpWords = 128;               // words per warp tile (4 per lane)
+constexpr int kB5WarpBytes = kB5WarpWords * kB5Nt;        // 3456
+constexpr int kB5WarpVecs = kB5WarpBytes / 16;            // 216 uint4
+constexpr int kB5SmemPerWarp = kB5WarpBytes + 16;         // one padding vector: lane 31 reads one word past its group
+constexpr int kB5Warps = 8;                               // warps per CTA
+constexpr uint32_t kB5Mul = (1u << 16) | (5u << 8) | 25u; // 0x010519
+
+// 4 ASCII bytes -> 4 base-5 digits.  The byte's low 3 bits index the 8-entry LUT held in two registers.
+__device__ __forceinline__ uint32_t b5_digits4(uint32_t x)
+{
+    // nibble-pack the four 3-bit indices: byte0 = i0 | i1<<4, byte2 = i2 | i3<<4 (bit 3 / 7 come from bit 7 of
+    // an ASCII byte, i.e. 0, so PRMT's sign-replicate selector bit stays clear)
+    uint32_t t = (x & 0x87878787u) | ((x >> 4) & 0x78787878u);
+    uint32_t sel = __byte_perm(t, 0u, 0x4420);
+    return __byte_perm(0x01000000u, 0x03040202u, sel);      // idx: 0,1(A),2 -> 0; 3(C) -> 1; 4(T),5(U) -> 2; 6(N) -> 4; 7(G) -> 3
+}
+
+// 27 digits (bytes of d[0..6], byte 27 ignored) -> the packed word
+__device__ __forceinline__ uint2 b5_pack27(const uint32_t (&d)[7])
+{
+    auto byte2 = [](uint32_t p) { return __byte_perm(p, 0u, 0x4442); };     // [p.b2, 0, 0, 0]
+    auto byte3 = [](uint32_t p) { return __byte_perm(p, 0u, 0x4443); };
+    uint32_t e0 = byte2(d[0] * kB5Mul);
+    uint32_t e1 = byte2(__funnelshift_r(d[0], d[1], 24) * kB5Mul);
+    uint32_t e2 = byte2(__funnelshift_r(d[1], d[2], 16) * kB5Mul);
+    uint32_t e3 = byte3(d[2] * kB5Mul);
+    uint32_t e4 = byte2(d[3] * kB5Mul);
+    uint32_t e5 = byte2(__funnelshift_r(d[3], d[4], 24) * kB5Mul);
+    uint32_t e6 = byte2(__funnelshift_r(d[4], d[5], 16) * kB5Mul);
+    uint32_t e7 = byte3(d[5] * kB5Mul);
+    uint32_t e8 = byte2(d[6] * kB5Mul);
+    uint2 w;
+    w.x = e0 + (e1 << 7) + (e2 << 14) + (e3 << 21) + (e4 << 28);
+    w.y = (e4 >> 4) + (e5 << 3) + (e6 << 10) + (e7 << 17) + (e8 << 24);
+    return w;
+}
+
+// packed word -> 27 ASCII bytes in a[0..6] (byte 27 is 'A', to be replaced by the caller)
+__device__ __forceinline__ void b5_unpack27(uint2 w, uint32_t (&a)[7])
+{
+    uint32_t e[9];
+    e[0] = w.x & 0x7F;          e[1] = (w.x >> 7) & 0x7F;   e[2] = (w.x >> 14) & 0x7F;  e[3] = (w.x >> 21) & 0x7F;
+    e[4] = __funnelshift_r(w.x, w.y, 28) & 0x7F;
+    e[5] = (w.y >> 3) & 0x7F;   e[6] = (w.y >> 10) & 0x7F;  e[7] = (w.y >> 17) & 0x7F;  e[8] = (w.y >> 24) & 0x7F;
+    uint32_t s[9];                                   // 12-bit selector triples: a | b<<4 | c<<8
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+        uint32_t q = (e[t] * 205u) >> 10;            // e / 5   (exact for e < 1024)
+        uint32_t c = (e[t] * 41u) >> 10;             // e / 25  (exact for e < 128)
+        s[t] = e[t] + 11u * q + 176u * c;            // (e - 5q) + 16 (q - 5c) + 256 c
+    }
+    uint32_t n0 = s[0] + (s[1] << 12) + (s[2] << 24);
+    uint32_t n1 = (s[2] >> 8) + (s[3] << 4) + (s[4] << 16) + (s[5] << 28);
+    uint32_t n2 = (s[5] >> 4) + (s[6] << 8) + (s[7] << 20);
+    uint32_t n3 = s[8];
+    const uint32_t lo = 0x47544341u, hi = 0x0000004Eu;      // 'A','C','T','G' | 'N',0,0,0
+    a[0] = __byte_perm(lo, hi, n0);  a[1] = __byte_perm(lo, hi, n0 >> 16);
+    a[2] = __byte_perm(lo, hi, n1);  a[3] = __byte_perm(lo, hi, n1 >> 16);
+    a[4] = __byte_perm(lo, hi, n2);  a[5] = __byte_perm(lo, hi, n2 >> 16);
+    a[6] = __byte_perm(lo, hi, n3);
+}
+
+// ---- scalar paths for whatever the warp tiles do not cover (ragged end, unaligned buffers) -------------
+__device__ __forceinline__ uint32_t b5_digit(uint32_t byte) { return (uint32_t)(0x0304020201000000ull >> (8 * (byte & 7))) & 7u; }
+
+// words [first, total): bytes past len count as digit 0 (src/n_to_bits2.rs:59-70)
+__device__ __forceinline__ void b5_encode_scalar(const uint8_t *__restrict__ n, size_t len, uint64_t *__restrict__ out,
+                                                 size_t first, size_t total, size_t lane, size_t stride)
+{
+    for (size_t w = first + lane; w < total; w += stride) {
+        uint64_t word = 0;
+        size_t base = w * kB5Nt;
+#pragma unroll 1
+        for (int t = 0; t < 9; t++) {
+            size_t i = base + 3 * t;
+            uint32_t a = i < len ? b5_digit(n[i]) : 0u;
+            uint32_t b = i + 1 < len ? b5_digit(n[i + 1]) : 0u;
+            uint32_t c = i + 2 < len ? b5_digit(n[i + 2]) : 0u;
+            word |= (uint64_t)(a + 5 * b + 25 * c) << (7 * t);
+        }
+        out[w] = word;
+    }
+}
+
+__device__ __forceinline__ void b5_decode_scalar(const uint64_t *__restrict__ bits, uint8_t *__restrict__ out, size_t len,
+                                                 size_t first, size_t total, size_t lane, size_t stride)
+{
+    for (size_t w = first + lane; w < total; w += stride) {
+        uint64_t word = bits[w];
+        size_t base = w * kB5Nt;
+#pragma unroll 1
+        for (int t = 0; t < 9; t++) {
+            uint32_t e = (uint32_t)(word >> (7 * t)) & 0x7Fu;
+            uint32_t dig[3] = {e % 5u, (e / 5u) % 5u, e / 25u};
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                size_t i = base + 3 * t + k;
+                if (i < len) out[i] = (uint8_t)(0x0000004E47544341ull >> (8 * dig[k]));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// encode: grid of CTAs with kB5Warps warps; global warp g owns tile g while g < ntiles; warp `ntiles`
+// finishes words [ntiles*128, total_words) with the scalar path.  `in` must be 16-byte aligned when
+// ntiles > 0.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kB5Warps * 32)
+b5_encode_kernel(const uint8_t *__restrict__ in, uint64_t *__restrict__ out, size_t len, size_t ntiles, size_t total_words)
+{
+    __shared__ __align__(16) uint8_t smem[kB5Warps * kB5SmemPerWarp];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t g = (size_t)blockIdx.x * kB5Warps + warp;
+    if (g < ntiles) {
+        uint8_t *tile = smem + warp * kB5SmemPerWarp;
+        const uint8_t *src = in + g * kB5WarpBytes;
+        uint4 v[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) {                          // 216 vectors: 6 full rounds + 24 lanes
+            unsigned i = lane + 32 * k;
+            if (i < kB5WarpVecs) v[k] = ld_stream16(src + 16 * i);
+        }
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            unsigned i = lane + 32 * k;
+            if (i < kB5WarpVecs) *reinterpret_cast<uint4 *>(tile + 16 * i) = v[k];
+        }
+        __syncwarp();
+        const uint32_t *tw = reinterpret_cast<const uint32_t *>(tile);
+        const unsigned shift = ((kB5Nt * lane) & 3u) * 8u;     // same for all four words of a lane (864 % 4 == 0)
+        uint64_t *dst = out + g * kB5WarpWords;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const unsigned w0 = (kB5Nt * (lane + 32 * c)) >> 2;
+            uint32_t r[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) r[k] = tw[w0 + k];
+            uint32_t d[7];
+#pragma unroll
+            for (int k = 0; k < 7; k++) d[k] = b5_digits4(__funnelshift_r(r[k], r[k + 1], shift));
+            uint2 w = b5_pack27(d);
+            st_stream8(dst + lane + 32 * c, w.x, w.y);
+        }
+    } else if (g == ntiles) {
+        b5_encode_scalar(in, len, out, ntiles * kB5WarpWords, total_words, lane, 32);
+    }
+}
+
+// generic encode for buffers the tiled kernel cannot take (ASCII pointer not 16-byte aligned)
+__global__ void __launch_bounds__(256)
+b5_encode_scalar_kernel(const uint8_t *__restrict__ in, uint64_t *__restrict__ out, size_t len, size_t total_words)
+{
+    b5_encode_scalar(in, len, out, 0, total_words, (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// decode: same tiling; `out` must be 16-byte aligned when ntiles > 0.  Tiles cover only words whose 27
+// nucleotides are all wanted (27*128*ntiles <= len); the scalar warp writes the rest up to len.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kB5Warps * 32)
+b5_decode_kernel(const uint64_t *__restrict__ bits, uint8_t *__restrict__ out, size_t len, size_t ntiles, size_t total_words)
+{
+    __shared__ __align__(16) uint8_t smem[kB5Warps * kB5SmemPerWarp];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t g = (size_t)blockIdx.x * kB5Warps + warp;
+    if (g < ntiles) {
+        uint8_t *tile = smem + warp * kB5SmemPerWarp;
+        uint32_t *tw = reinterpret_cast<uint32_t *>(tile);
+        const uint64_t *src = bits + g * kB5WarpWords;
+        uint2 w[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) w[c] = ld_stream8(src + lane + 32 * c);
+        const unsigned own = lane & 3u;                         // = (-27*lane) mod 4: bytes until the lane's first owned word
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            uint32_t a[8];
+            {
+                uint32_t s[7];
+                b5_unpack27(w[c], s);
+#pragma unroll
+                for (int k = 0; k < 7; k++) a[k] = s[k];
+            }
+            // a lane owns the smem words that START inside its 27 bytes; the last of them also holds the first
+            // bytes of the next lane's group, fetched with one shuffle (lane 31 owns none of those: own == 3)
+            uint32_t next = __shfl_down_sync(0xFFFFFFFFu, a[0], 1);
+            a[6] = __byte_perm(a[6], next, 0x4210);             // bytes 24,25,26 + neighbour byte 0
+            a[7] = next >> 8;                                   // neighbour bytes 1,2,3
+            const unsigned w0 = (kB5Nt * (lane + 32 * c) + own) >> 2;
+#pragma unroll
+            for (int k = 0; k < 7; k++) {
+                uint32_t word = __funnelshift_r(a[k], a[k + 1], 8 * own);
+                if (k < 6 || own != 3) tw[w0 + k] = word;
+            }
+        }
+        __syncwarp();
+        uint8_t *dst = out + g * kB5WarpBytes;
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            unsigned i = lane + 32 * k;
+            if (i < kB5WarpVecs) st_stream16(dst + 16 * i, *reinterpret_cast<const uint4 *>(tile + 16 * i));
+        }
+    } else if (g == ntiles) {
+        b5_decode_scalar(bits, out, len, ntiles * kB5WarpWords, total_words, lane, 32);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+b5_decode_scalar_kernel(const uint64_t *__restrict__ bits, uint8_t *__restrict__ out, size_t len, size_t total_words)
+{
+    b5_decode_scalar(bits, out, len, 0, total_words, (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
+}
+
+// synthetic 5-letter data, bit-identical to the host generator used by the tests:
+// alphabet 5 = "ACGTN"[(b*5)>>8], alphabet 12 = "ACGTUNacgtun"[(b*12)>>8]
+__global__ void b5_generate_kernel(uint8_t *__restrict__ out, size_t offset, size_t len, uint64_t seed, int alphabet)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
+        size_t gidx = offset + i;
+        uint64_t h = mix64(seed, gidx >> 3);
+        uint32_t b = (uint32_t)(h >> (8 * (gidx & 7))) & 0xFFu;
+        uint32_t k = alphabet == 5 ? (b * 5u) >> 8 : (b * 12u) >> 8;
+        const uint64_t lo = 0x63614E5554474341ull;               // A C G T U N a c
+        const uint32_t hi = 0x6E757467u;                         // g t u n
+        uint32_t ch;
+        if (alphabet == 5) ch = k < 4 ? (uint32_t)(lo >> (8 * k)) & 0xFFu : (uint32_t)'N';
+        else ch = k < 8 ? (uint32_t)(lo >> (8 * k)) & 0xFFu : (hi >> (8 * (k - 8))) & 0xFFu;
+        out[i] = (uint8_t)ch;
+    }
+}
+
+}  // namespace cn

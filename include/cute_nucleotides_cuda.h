@@ -78,6 +78,20 @@ CN_API int cn_encode_device(const void *d_n, size_t len, void *d_out, void *stre
 /* d_bits 8-byte aligned; d_out any alignment (16-byte aligned takes the fast path). */
 CN_API int cn_decode_device(const void *d_bits, size_t nwords, size_t len, void *d_out, void *stream);
 
+/* ---- base-5 codec: {A,C,T/U,G,N} -> digits 0..4, 3 digits -> 7 bits, 27 nucleotides per u64 ------------ */
+/* (len / 27) + (len % 27 != 0): words produced by n_to_bits2_* (src/n_to_bits2.rs:38, :121). */
+CN_API size_t cn_words2_for_len(size_t len);
+/* n_to_bits2_{lut,pext}(n) -- src/n_to_bits2.rs:37, 118.  `out` receives cn_words2_for_len(len) words; the digit
+ * of a byte is looked up by its low 3 bits like the reference's pshufb LUT (:127-136). */
+CN_API int cn_n_to_bits2_host(const uint8_t *n, size_t len, uint64_t *out);
+/* bits_to_n2_{lut,pdep}(bits, len) -- src/n_to_bits2.rs:78, 196.  CN_ERR_LENGTH when len > 27 * nwords (:79-81). */
+CN_API int cn_bits_to_n2_host(const uint64_t *bits, size_t nwords, size_t len, uint8_t *out);
+/* Device-resident pair; the ASCII side takes the tiled fast path when 16-byte aligned. */
+CN_API int cn_encode2_device(const void *d_n, size_t len, void *d_out, void *stream);
+CN_API int cn_decode2_device(const void *d_bits, size_t nwords, size_t len, void *d_out, void *stream);
+/* Synthetic 5-letter data: alphabet 5 = {A,C,G,T,N}, alphabet 12 = {A,C,G,T,U,N,a,c,g,t,u,n}. */
+CN_API int cn_generate2_device(void *d_out, size_t offset, size_t len, uint64_t seed, int alphabet, void *stream);
+
 /* ---- harness helpers (tests, bench, the C++/Rust harnesses; not needed by a plain caller) ------- */
 /* Deterministic synthetic data, bit-identical to the host generator used by the tests:
  * alphabet 4 = uniform {A,C,G,T}; alphabet 10 = {A,C,G,T,U,a,c,g,t,u}.  `offset` (multiple of 8) is the

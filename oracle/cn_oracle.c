@@ -392,3 +392,165 @@ CN_EXPORT int oracle_cpu_ok(void)
     __builtin_cpu_init();
     return __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2") && __builtin_cpu_supports("pclmul");
 }
+
+/* ========================================================================================== */
+/* Base-5 codec: {A, C, T/U, G, N} -> digits 0..4, three digits -> 7 bits (a + 5b + 25c),      */
+/* nine triplets (27 nucleotides) per u64.  Restates src/n_to_bits2.rs.                        */
+/* ========================================================================================== */
+static uint8_t g_byte_lut2[256];
+static const uint8_t g_bits_lut2[8] = { 'A', 'C', 'T', 'G', 'N', 0, 0, 0 };   /* src/n_to_bits2.rs:25-33 (5 entries) */
+static pthread_once_t g_once2 = PTHREAD_ONCE_INIT;
+
+static void init_tables2(void)
+{   /* src/n_to_bits2.rs:8-23 */
+    memset(g_byte_lut2, 0, sizeof g_byte_lut2);
+    g_byte_lut2['a'] = 0; g_byte_lut2['A'] = 0;
+    g_byte_lut2['c'] = 1; g_byte_lut2['C'] = 1;
+    g_byte_lut2['t'] = 2; g_byte_lut2['T'] = 2;
+    g_byte_lut2['u'] = 2; g_byte_lut2['U'] = 2;
+    g_byte_lut2['g'] = 3; g_byte_lut2['G'] = 3;
+    g_byte_lut2['n'] = 4; g_byte_lut2['N'] = 4;
+}
+
+CN_EXPORT size_t oracle_words2_for_len(size_t len)
+{   /* src/n_to_bits2.rs:38 */
+    return len / 27 + ((len % 27) ? 1 : 0);
+}
+
+/* src/n_to_bits2.rs:37-74 n_to_bits2_lut */
+CN_EXPORT void oracle_n_to_bits2_lut(const uint8_t *n, size_t len, uint64_t *out)
+{
+    pthread_once(&g_once2, init_tables2);
+    size_t words = oracle_words2_for_len(len);
+    for (size_t w = 0; w < words; w++) out[w] = 0;
+    size_t triplets = len / 3;
+    for (size_t t = 0; t < triplets; t++) {
+        const uint8_t *p = n + 3 * t;
+        uint64_t enc = (uint64_t)g_byte_lut2[p[0]] + 5u * g_byte_lut2[p[1]] + 25u * g_byte_lut2[p[2]];
+        out[t / 9] |= enc << ((t % 9) * 7);
+    }
+    size_t left = len % 3;                          /* :59-70 ragged last triplet */
+    if (left) {
+        const uint8_t *p = n + 3 * triplets;
+        uint64_t enc = g_byte_lut2[p[0]];
+        if (left >= 2) enc += 5u * g_byte_lut2[p[1]];
+        out[triplets / 9] |= enc << ((triplets % 9) * 7);
+    }
+}
+
+/* src/n_to_bits2.rs:78-107 bits_to_n2_lut.  Decodes whole triplets, so `out` needs
+ * 3*ceil(len/3) bytes (the reference allocates 27*nwords, :87); the caller keeps `len`.
+ * Returns 1 where the reference panics (:79-81).  A 7-bit field above 124 cannot come from the
+ * encoder; the reference would index BITS_LUT out of bounds there, the oracle yields 0 bytes. */
+CN_EXPORT int oracle_bits_to_n2_lut(const uint64_t *bits, size_t nwords, size_t len, uint8_t *out)
+{
+    if (len > nwords * 27) return 1;
+    size_t triplets = len / 3 + ((len % 3) ? 1 : 0);
+    for (size_t t = 0; t < triplets; t++) {
+        unsigned cur = (unsigned)(bits[t / 9] >> ((t % 9) * 7)) & 0x7Fu;
+        out[3 * t] = g_bits_lut2[cur % 5];
+        out[3 * t + 1] = g_bits_lut2[(cur / 5) % 5];
+        out[3 * t + 2] = g_bits_lut2[(cur / 25) & 7];
+    }
+    return 0;
+}
+
+/* src/n_to_bits2.rs:118-189 n_to_bits2_pext: pshufb LUT on the low 3 ASCII bits (:127-136),
+ * permutevar8x32 to make both halves lane-local, two pshufb to split a / (b,c), maddubs by (5,25),
+ * add, pext(0x007F..) to squeeze 16-bit lanes to 7 bits.  Vector body covers (len-5)/27 words
+ * (:120, the 32-byte load must stay inside the slice), the rest goes through n_to_bits2_lut. */
+__attribute__((target("avx2,bmi2")))
+CN_EXPORT void oracle_n_to_bits2_pext(const uint8_t *n, size_t len, uint64_t *out)
+{
+    size_t body = len < 5 ? 0 : (len - 5) / 27;
+    size_t words = oracle_words2_for_len(len);
+    long long lutq = 0;
+    lutq |= 0ll << ((('A') & 7) << 3);
+    lutq |= 1ll << ((('C') & 7) << 3);
+    lutq |= 2ll << ((('T') & 7) << 3);
+    lutq |= 2ll << ((('U') & 7) << 3);
+    lutq |= 3ll << ((('G') & 7) << 3);
+    lutq |= 4ll << ((('N') & 7) << 3);
+    const __m256i lut = _mm256_set1_epi64x(lutq);
+    const __m256i bridge = _mm256_set_epi32(6, 5, 4, 3, 3, 2, 1, 0);
+    const __m256i first = _mm256_set_epi16(-1, -1, -1, -1, (short)0xFF1C, (short)0xFF19, (short)0xFF16, (short)0xFF13,
+                                           -1, -1, -1, (short)0xFF0C, (short)0xFF09, (short)0xFF06, (short)0xFF03, (short)0xFF00);
+    const __m256i rest = _mm256_set_epi16(-1, -1, -1, -1, 0x1E1D, 0x1B1A, 0x1817, 0x1514,
+                                          -1, -1, -1, 0x0E0D, 0x0B0A, 0x0807, 0x0504, 0x0201);
+    const __m256i w5_25 = _mm256_set1_epi16(0x1905);
+    const uint64_t squeeze = 0x007F007F007F007Full;
+    const uint8_t *p = n;
+    for (size_t w = 0; w < body; w++, p += 27) {
+        __m256i v = _mm256_shuffle_epi8(lut, _mm256_loadu_si256((const __m256i *)p));
+        v = _mm256_permutevar8x32_epi32(v, bridge);
+        __m256i a = _mm256_shuffle_epi8(v, first);
+        __m256i bc = _mm256_maddubs_epi16(_mm256_shuffle_epi8(v, rest), w5_25);
+        __m256i e = _mm256_add_epi16(a, bc);
+        uint64_t q0 = (uint64_t)_mm256_extract_epi64(e, 0), q1 = (uint64_t)_mm256_extract_epi64(e, 1),
+                 q2 = (uint64_t)_mm256_extract_epi64(e, 2);
+        out[w] = _pext_u64(q0, squeeze) | (q1 << 28) | (_pext_u64(q2, squeeze) << 35);
+    }
+    if (body < words) oracle_n_to_bits2_lut(n + body * 27, len - body * 27, out + body);
+}
+
+/* src/n_to_bits2.rs:196-268 bits_to_n2_pdep: pdep(0x7F7F..) pads 7-bit fields to bytes, pshufb widens
+ * to 16 bits, division / remainder by 5 and 25 through 16-bit reciprocal multiplies (:209-211,241-247),
+ * three pshufb + or to interleave a,b,c, permutevar8x32 to close the lane gap, pshufb(lut).
+ * Stores 32 bytes per word at stride 27: `out` needs 27*nwords + 5 bytes (:201). */
+__attribute__((target("avx2,bmi2")))
+CN_EXPORT int oracle_bits_to_n2_pdep(const uint64_t *bits, size_t nwords, size_t len, uint8_t *out)
+{
+    if (len > nwords * 27) return 1;
+    const uint64_t pad = 0x7F7F7F7F7F7F7F7Full;
+    const __m256i widen = _mm256_set_epi16(-1, -1, -1, (short)0xFF04, (short)0xFF03, (short)0xFF02, (short)0xFF01, (short)0xFF00,
+                                           -1, -1, -1, -1, (short)0xFF03, (short)0xFF02, (short)0xFF01, (short)0xFF00);
+    const __m256i five = _mm256_set1_epi16(5);
+    const __m256i inv5 = _mm256_set1_epi16((short)((1u << 16) / 5 + 1));
+    const __m256i inv25 = _mm256_set1_epi16((short)((1u << 16) / 25 + 1));
+    const __m256i sel_a = _mm256_set_epi64x((long long)0xFFFFFF08FFFF06FFull, (long long)0xFF04FFFF02FFFF00ull,
+                                            (long long)0xFFFFFF08FFFF06FFull, (long long)0xFF04FFFF02FFFF00ull);
+    const __m256i sel_b = _mm256_set_epi64x((long long)0xFFFF08FFFF06FFFFull, (long long)0x04FFFF02FFFF00FFull,
+                                            (long long)0xFFFF08FFFF06FFFFull, (long long)0x04FFFF02FFFF00FFull);
+    const __m256i sel_c = _mm256_set_epi64x((long long)0xFF08FFFF06FFFF04ull, (long long)0xFFFF02FFFF00FFFFull,
+                                            (long long)0xFF08FFFF06FFFF04ull, (long long)0xFFFF02FFFF00FFFFull);
+    const __m256i close_gap = _mm256_set_epi32(7, 7, 6, 5, 4, 2, 1, 0);
+    const __m256i lut = _mm256_set1_epi64x((long long)('A' | ('C' << 8) | ('T' << 16) | ((uint64_t)'G' << 24) | ((uint64_t)'N' << 32)));
+    uint8_t *p = out;
+    for (size_t w = 0; w < nwords; w++, p += 27) {
+        int64_t cur = (int64_t)bits[w];
+        int64_t lo = (int64_t)_pdep_u64((uint64_t)cur, pad);
+        int64_t hi = ((cur >> 56) << 32) | (lo >> 32);
+        __m256i v = _mm256_shuffle_epi8(_mm256_set_epi64x(0, hi, 0, lo), widen);
+        __m256i f5 = _mm256_mullo_epi16(v, inv5), f25 = _mm256_mullo_epi16(v, inv25);
+        __m256i a = _mm256_shuffle_epi8(_mm256_mulhi_epu16(f5, five), sel_a);
+        __m256i b = _mm256_shuffle_epi8(_mm256_mulhi_epu16(f25, five), sel_b);
+        __m256i c = _mm256_shuffle_epi8(_mm256_mulhi_epu16(v, inv25), sel_c);
+        __m256i abc = _mm256_permutevar8x32_epi32(_mm256_or_si256(_mm256_or_si256(a, b), c), close_gap);
+        _mm256_storeu_si256((__m256i *)p, _mm256_shuffle_epi8(lut, abc));
+    }
+    return 0;
+}
+
+/* synthetic 5-letter data: "ACGTN"[(lane_byte * 5) >> 8] (alphabet 5), "ACGTUNacgtun" (alphabet 12) */
+CN_EXPORT int oracle_generate2(uint8_t *out, size_t offset, size_t len, uint64_t seed, int alphabet)
+{
+    static const char a5[] = "ACGTN", a12[] = "ACGTUNacgtun";
+    if (alphabet != 5 && alphabet != 12) return 3;
+    size_t i = 0;
+    while (i < len) {
+        size_t g = offset + i;
+        uint64_t h = mix64(seed, g >> 3);
+        for (unsigned lane = (unsigned)(g & 7); lane < 8 && i < len; lane++, i++) {
+            unsigned b = (unsigned)(h >> (8 * lane)) & 0xFFu;
+            out[i] = (uint8_t)(alphabet == 5 ? a5[(b * 5) >> 8] : a12[(b * 12) >> 8]);
+        }
+    }
+    return 0;
+}
+
+/* what bits_to_n2(n_to_bits2(x)) must equal: upper case, U -> T */
+CN_EXPORT void oracle_canonical2(const uint8_t *n, size_t len, uint8_t *out)
+{
+    pthread_once(&g_once2, init_tables2);
+    for (size_t i = 0; i < len; i++) out[i] = g_bits_lut2[g_byte_lut2[n[i]]];
+}

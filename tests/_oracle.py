@@ -14,6 +14,8 @@ ORACLE_SO = os.path.join(ORACLE_DIR, "libcn_oracle.so")
 
 ENCODERS = ("lut", "pext", "shift", "movemask", "mul")
 DECODERS = ("lut", "shuffle", "pdep", "clmul")
+ENCODERS2 = ("lut", "pext")          # src/n_to_bits2.rs
+DECODERS2 = ("lut", "pdep")
 
 
 def build_oracle() -> str:
@@ -44,6 +46,15 @@ class Oracle:
         L.oracle_generate_words.restype, L.oracle_generate_words.argtypes = None, [c_void_p, c_size_t, c_size_t, c_uint64]
         L.oracle_canonical.restype, L.oracle_canonical.argtypes = None, [c_void_p, c_size_t, c_void_p]
         L.oracle_cpu_ok.restype = c_int
+        L.oracle_words2_for_len.restype, L.oracle_words2_for_len.argtypes = c_size_t, [c_size_t]
+        for v in ENCODERS2:
+            f = getattr(L, f"oracle_n_to_bits2_{v}")
+            f.restype, f.argtypes = None, [c_void_p, c_size_t, c_void_p]
+        for v in DECODERS2:
+            f = getattr(L, f"oracle_bits_to_n2_{v}")
+            f.restype, f.argtypes = c_int, [c_void_p, c_size_t, c_size_t, c_void_p]
+        L.oracle_generate2.restype, L.oracle_generate2.argtypes = c_int, [c_void_p, c_size_t, c_size_t, c_uint64, c_int]
+        L.oracle_canonical2.restype, L.oracle_canonical2.argtypes = None, [c_void_p, c_size_t, c_void_p]
         self.simd_ok = bool(L.oracle_cpu_ok())
         self.threads = os.cpu_count() or 1
 
@@ -115,3 +126,32 @@ class Oracle:
     def count_invalid(self, n) -> int:
         a = self._u8(n)
         return self.lib.oracle_count_invalid(a.ctypes.data, a.size)
+
+    # -- base-5 codec (src/n_to_bits2.rs) --------------------------------------------------------------
+    def words2_for_len(self, length: int) -> int:
+        return self.lib.oracle_words2_for_len(length)
+
+    def n_to_bits2(self, n, variant: str = "lut") -> np.ndarray:
+        a = self._u8(n)
+        out = np.empty(self.words2_for_len(a.size), dtype=np.uint64)
+        getattr(self.lib, f"oracle_n_to_bits2_{variant}")(a.ctypes.data, a.size, out.ctypes.data)
+        return out
+
+    def bits_to_n2(self, bits, length: int, variant: str = "lut") -> bytes:
+        w = np.ascontiguousarray(bits, dtype=np.uint64)
+        out = np.empty(27 * w.size + 8, dtype=np.uint8)          # decoders write whole triplets / 32-byte stores
+        rc = getattr(self.lib, f"oracle_bits_to_n2_{variant}")(w.ctypes.data, w.size, length, out.ctypes.data)
+        if rc == 1:
+            raise ValueError("The length is greater than the number of nucleotides!")
+        return out[:length].tobytes()
+
+    def generate2(self, length: int, seed: int, alphabet: int = 5, offset: int = 0) -> np.ndarray:
+        out = np.empty(length, dtype=np.uint8)
+        assert self.lib.oracle_generate2(out.ctypes.data, offset, length, seed, alphabet) == 0
+        return out
+
+    def canonical2(self, n) -> bytes:
+        a = self._u8(n)
+        out = np.empty(a.size, dtype=np.uint8)
+        self.lib.oracle_canonical2(a.ctypes.data, a.size, out.ctypes.data)
+        return out.tobytes()
