@@ -220,6 +220,11 @@ int decode_device(const void *d_bits, size_t nwords, size_t len, void *d_out, cu
 }
 
 // ---- base-5 codec (src/n_to_bits2.rs) ----------------------------------------------------------------
+// Tile staging of the base-5 kernels: bit 0 = cp.async.bulk (TMA) tile load in encode, bit 1 = TMA tile store in
+// decode.  Measured on B200 at 10 GiB (profiles/codec5_r01.json): LDG/STS staging 6118 / 6500 GB/s, TMA 6870 / 6712 GB/s,
+// so TMA is the default; CN_B5_TMA=0..3 selects the alternatives for A/B runs.
+const int g_b5_tma = std::getenv("CN_B5_TMA") ? std::atoi(std::getenv("CN_B5_TMA")) : 3;
+
 inline size_t words2_for_len(size_t len) { return len / 27 + ((len % 27) ? 1 : 0); }
 
 int encode2_device(const void *d_n, size_t len, void *d_out, cudaStream_t s)
@@ -230,11 +235,12 @@ int encode2_device(const void *d_n, size_t len, void *d_out, cudaStream_t s)
     const size_t total = words2_for_len(len);
     const uint8_t *in = static_cast<const uint8_t *>(d_n);
     uint64_t *out = static_cast<uint64_t *>(d_out);
-    if ((addr(d_n) & 15) == 0) {
+    if ((addr(d_n) & 15) == 0 && (addr(d_out) & 31) == 0) {                  // 128-bit ASCII loads, 256-bit packed stores
         const size_t ntiles = (len / 27) / cn::kB5WarpWords;                 // tiles of complete words
         const size_t blocks = (ntiles + 1 + cn::kB5Warps - 1) / cn::kB5Warps;
         if (blocks > kMaxGrid) return fail(CN_ERR_ARG, "cn_encode2_device: input too large for one launch");
-        cn::b5_encode_kernel<<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(in, out, len, ntiles, total);
+        if (g_b5_tma & 1) cn::b5_encode_kernel<true><<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(in, out, len, ntiles, total);
+        else cn::b5_encode_kernel<false><<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(in, out, len, ntiles, total);
     } else {
         size_t blocks = (total + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;
@@ -255,11 +261,12 @@ int decode2_device(const void *d_bits, size_t nwords, size_t len, void *d_out, c
     const size_t total = words2_for_len(len);
     const uint64_t *bits = static_cast<const uint64_t *>(d_bits);
     uint8_t *out = static_cast<uint8_t *>(d_out);
-    if ((addr(d_out) & 15) == 0) {
+    if ((addr(d_out) & 15) == 0 && (addr(d_bits) & 31) == 0) {
         const size_t ntiles = (len / 27) / cn::kB5WarpWords;
         const size_t blocks = (ntiles + 1 + cn::kB5Warps - 1) / cn::kB5Warps;
         if (blocks > kMaxGrid) return fail(CN_ERR_ARG, "cn_decode2_device: input too large for one launch");
-        cn::b5_decode_kernel<<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(bits, out, len, ntiles, total);
+        if (g_b5_tma & 2) cn::b5_decode_kernel<true><<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(bits, out, len, ntiles, total);
+        else cn::b5_decode_kernel<false><<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(bits, out, len, ntiles, total);
     } else {
         size_t blocks = (total + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;

@@ -4,19 +4,22 @@
 //
 // Shape of the problem on a GPU: 27 ASCII bytes <-> 8 packed bytes (1.296 B of HBM traffic per
 // nucleotide), and 27-byte groups are not aligned to anything -- but 32 groups are 864 bytes = 54 x 16 B.
-// So a WARP owns a tile of 4 x 32 words (3456 ASCII bytes, 16-byte aligned): global memory is touched only
-// with coalesced 128-bit accesses, the tile is staged in a warp-private slice of shared memory (only
-// __syncwarp, no block barrier), and each lane converts whole words out of / into shared memory.
+// So a WARP owns a tile of 128 words (3456 ASCII bytes, 16-byte aligned): global memory is touched only
+// with coalesced 128/256-bit accesses, the tile is staged in a warp-private slice of shared memory (only
+// __syncwarp, no block barrier), and each LANE owns 4 consecutive words = 108 ASCII bytes = exactly 27
+// aligned shared-memory words.  Lanes are 27 words apart, and 27 is coprime with the 32 banks, so every
+// LDS.32 / STS.32 is conflict-free, and because 108 is a multiple of 4 every byte offset inside a lane's
+// block is a compile-time constant (no per-lane funnel shifts).
 //
-//   encode, per lane and word: 8 LDS.32 + funnel shifts realign the lane's 27 bytes; digits come from a
+//   encode, per lane: 27 LDS.32; digits come from a
 //     PRMT lookup on the low 3 ASCII bits (exactly the reference's pshufb LUT, src/n_to_bits2.rs:127-136:
 //     'A'&7=1 'C'&7=3 'T'&7=4 'U'&7=5 'N'&7=6 'G'&7=7, case-insensitive for free); a triplet sitting in
 //     bytes 0..2 (or 1..3) of a register is ONE multiply: x * (1<<16 | 5<<8 | 25) leaves a+5b+25c in
 //     byte 2 (byte 3) with no carries -- the GPU analogue of maddubs(5,25)+add (:160-163).
 //   decode, per lane and word: q = e*205>>10 (= e/5), c = e*41>>10 (= e/25), and the three digits as PRMT
 //     selector nibbles are e + 11q + 176c; PRMT against 'A','C','T','G','N' emits the letters (the
-//     reciprocal-multiply idea of :209-211,241-247 on 32-bit registers); a lane's 27 bytes are merged with
-//     its neighbour's first bytes by one warp shuffle so shared memory is written in whole words.
+//     reciprocal-multiply idea of :209-211,241-247 on 32-bit registers); the four 27-byte strings of a lane
+//     are spliced into 27 whole words with constant funnel shifts and written with 27 STS.32.
 #pragma once
 #include "codec_kernels.cuh"
 
@@ -26,9 +29,38 @@ constexpr int kB5Nt = 27;                       // nucleotides per word
 constexpr int kB5WarpWords = 128;               // words per warp tile (4 per lane)
 constexpr int kB5WarpBytes = kB5WarpWords * kB5Nt;        // 3456
 constexpr int kB5WarpVecs = kB5WarpBytes / 16;            // 216 uint4
-constexpr int kB5SmemPerWarp = kB5WarpBytes + 16;         // one padding vector: lane 31 reads one word past its group
+constexpr int kB5SmemPerWarp = kB5WarpBytes;
 constexpr int kB5Warps = 8;                               // warps per CTA
 constexpr uint32_t kB5Mul = (1u << 16) | (5u << 8) | 25u; // 0x010519
+
+// ---- cp.async.bulk (TMA 1-D bulk copy) + mbarrier helpers ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+                 ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *gdst, const void *smem_src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_addr(smem_src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // 4 ASCII bytes -> 4 base-5 digits.  The byte's low 3 bits index the 8-entry LUT held in two registers.
 __device__ __forceinline__ uint32_t b5_digits4(uint32_t x)
@@ -40,24 +72,23 @@ __device__ __forceinline__ uint32_t b5_digits4(uint32_t x)
     return __byte_perm(0x01000000u, 0x03040202u, sel);      // idx: 0,1(A),2 -> 0; 3(C) -> 1; 4(T),5(U) -> 2; 6(N) -> 4; 7(G) -> 3
 }
 
-// 27 digits (bytes of d[0..6], byte 27 ignored) -> the packed word
-__device__ __forceinline__ uint2 b5_pack27(const uint32_t (&d)[7])
+// 108 digits (the bytes of d[0..26]) -> four packed words.  Triplet j sits at bytes 3j..3j+2; the pattern repeats
+// every 3 registers: offset 0 (product byte 2), 3 and 2 (funnel shift first), 1 (product byte 3).
+__device__ __forceinline__ void b5_pack108(const uint32_t (&d)[27], uint2 (&w)[4])
 {
-    auto byte2 = [](uint32_t p) { return __byte_perm(p, 0u, 0x4442); };     // [p.b2, 0, 0, 0]
-    auto byte3 = [](uint32_t p) { return __byte_perm(p, 0u, 0x4443); };
-    uint32_t e0 = byte2(d[0] * kB5Mul);
-    uint32_t e1 = byte2(__funnelshift_r(d[0], d[1], 24) * kB5Mul);
-    uint32_t e2 = byte2(__funnelshift_r(d[1], d[2], 16) * kB5Mul);
-    uint32_t e3 = byte3(d[2] * kB5Mul);
-    uint32_t e4 = byte2(d[3] * kB5Mul);
-    uint32_t e5 = byte2(__funnelshift_r(d[3], d[4], 24) * kB5Mul);
-    uint32_t e6 = byte2(__funnelshift_r(d[4], d[5], 16) * kB5Mul);
-    uint32_t e7 = byte3(d[5] * kB5Mul);
-    uint32_t e8 = byte2(d[6] * kB5Mul);
-    uint2 w;
-    w.x = e0 + (e1 << 7) + (e2 << 14) + (e3 << 21) + (e4 << 28);
-    w.y = (e4 >> 4) + (e5 << 3) + (e6 << 10) + (e7 << 17) + (e8 << 24);
-    return w;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        uint32_t e[9];
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+            const int j = 9 * g + t, m = 3 * (j >> 2), r = j & 3;
+            uint32_t v = r == 0 ? d[m] : r == 1 ? __funnelshift_r(d[m], d[m + 1], 24)
+                       : r == 2 ? __funnelshift_r(d[m + 1], d[m + 2], 16) : d[m + 2];
+            e[t] = __byte_perm(v * kB5Mul, 0u, r == 3 ? 0x4443 : 0x4442);       // [a+5b+25c, 0, 0, 0]
+        }
+        w[g].x = e[0] + (e[1] << 7) + (e[2] << 14) + (e[3] << 21) + (e[4] << 28);
+        w[g].y = (e[4] >> 4) + (e[5] << 3) + (e[6] << 10) + (e[7] << 17) + (e[8] << 24);
+    }
 }
 
 // packed word -> 27 ASCII bytes in a[0..6] (byte 27 is 'A', to be replaced by the caller)
@@ -83,6 +114,22 @@ __device__ __forceinline__ void b5_unpack27(uint2 w, uint32_t (&a)[7])
     a[2] = __byte_perm(lo, hi, n1);  a[3] = __byte_perm(lo, hi, n1 >> 16);
     a[4] = __byte_perm(lo, hi, n2);  a[5] = __byte_perm(lo, hi, n2 >> 16);
     a[6] = __byte_perm(lo, hi, n3);
+}
+
+// four 27-byte strings (a[g][0..6], byte 27 of each is filler) -> 27 words holding the 108 bytes back to back
+__device__ __forceinline__ void b5_splice108(const uint32_t (&a)[4][7], uint32_t (&o)[27])
+{
+#pragma unroll
+    for (int k = 0; k < 6; k++) o[k] = a[0][k];
+    o[6] = __byte_perm(a[0][6], a[1][0], 0x4210);                 // bytes 24,25,26 | next 0
+#pragma unroll
+    for (int k = 0; k < 6; k++) o[7 + k] = __funnelshift_r(a[1][k], a[1][k + 1], 8);
+    o[13] = __byte_perm(a[1][6], a[2][0], 0x5421);                // bytes 25,26 | next 0,1
+#pragma unroll
+    for (int k = 0; k < 6; k++) o[14 + k] = __funnelshift_r(a[2][k], a[2][k + 1], 16);
+    o[20] = __byte_perm(a[2][6], a[3][0], 0x6542);                // byte 26 | next 0,1,2
+#pragma unroll
+    for (int k = 0; k < 6; k++) o[21 + k] = __funnelshift_r(a[3][k], a[3][k + 1], 24);
 }
 
 // ---- scalar paths for whatever the warp tiles do not cover (ragged end, unaligned buffers) -------------
@@ -131,42 +178,48 @@ __device__ __forceinline__ void b5_decode_scalar(const uint64_t *__restrict__ bi
 // finishes words [ntiles*128, total_words) with the scalar path.  `in` must be 16-byte aligned when
 // ntiles > 0.
 // ------------------------------------------------------------------------------------------------------
+template <bool TMA>
 __global__ void __launch_bounds__(kB5Warps * 32)
 b5_encode_kernel(const uint8_t *__restrict__ in, uint64_t *__restrict__ out, size_t len, size_t ntiles, size_t total_words)
 {
-    __shared__ __align__(16) uint8_t smem[kB5Warps * kB5SmemPerWarp];
+    __shared__ __align__(128) uint8_t smem[kB5Warps * kB5SmemPerWarp];
+    __shared__ uint64_t bars[kB5Warps];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t g = (size_t)blockIdx.x * kB5Warps + warp;
     if (g < ntiles) {
         uint8_t *tile = smem + warp * kB5SmemPerWarp;
         const uint8_t *src = in + g * kB5WarpBytes;
-        uint4 v[7];
+        if constexpr (TMA) {
+            // one lane asks the TMA unit for the whole 3456-byte tile; nobody spends LSU slots or registers on it
+            if (lane == 0) {
+                mbar_init(&bars[warp], 1);
+                mbar_expect_tx(&bars[warp], kB5WarpBytes);
+                bulk_load(tile, src, kB5WarpBytes, &bars[warp]);
+            }
+            __syncwarp();
+            mbar_wait(&bars[warp], 0);
+        } else {
+            uint4 v[7];
 #pragma unroll
-        for (int k = 0; k < 7; k++) {                          // 216 vectors: 6 full rounds + 24 lanes
-            unsigned i = lane + 32 * k;
-            if (i < kB5WarpVecs) v[k] = ld_stream16(src + 16 * i);
+            for (int k = 0; k < 7; k++) {                      // 216 vectors: 6 full rounds + 24 lanes
+                unsigned i = lane + 32 * k;
+                if (i < kB5WarpVecs) v[k] = ld_stream16(src + 16 * i);
+            }
+#pragma unroll
+            for (int k = 0; k < 7; k++) {
+                unsigned i = lane + 32 * k;
+                if (i < kB5WarpVecs) *reinterpret_cast<uint4 *>(tile + 16 * i) = v[k];
+            }
+            __syncwarp();
         }
+        const uint32_t *tw = reinterpret_cast<const uint32_t *>(tile) + 27 * lane;     // this lane's 108 bytes
+        uint32_t d[27];
 #pragma unroll
-        for (int k = 0; k < 7; k++) {
-            unsigned i = lane + 32 * k;
-            if (i < kB5WarpVecs) *reinterpret_cast<uint4 *>(tile + 16 * i) = v[k];
-        }
-        __syncwarp();
-        const uint32_t *tw = reinterpret_cast<const uint32_t *>(tile);
-        const unsigned shift = ((kB5Nt * lane) & 3u) * 8u;     // same for all four words of a lane (864 % 4 == 0)
-        uint64_t *dst = out + g * kB5WarpWords;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const unsigned w0 = (kB5Nt * (lane + 32 * c)) >> 2;
-            uint32_t r[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) r[k] = tw[w0 + k];
-            uint32_t d[7];
-#pragma unroll
-            for (int k = 0; k < 7; k++) d[k] = b5_digits4(__funnelshift_r(r[k], r[k + 1], shift));
-            uint2 w = b5_pack27(d);
-            st_stream8(dst + lane + 32 * c, w.x, w.y);
-        }
+        for (int k = 0; k < 27; k++) d[k] = b5_digits4(tw[k]);
+        uint2 w[4];
+        b5_pack108(d, w);
+        st_stream32(out + g * kB5WarpWords + 4 * lane, make_uint4(w[0].x, w[0].y, w[1].x, w[1].y),
+                    make_uint4(w[2].x, w[2].y, w[3].x, w[3].y));
     } else if (g == ntiles) {
         b5_encode_scalar(in, len, out, ntiles * kB5WarpWords, total_words, lane, 32);
     }
@@ -183,47 +236,37 @@ b5_encode_scalar_kernel(const uint8_t *__restrict__ in, uint64_t *__restrict__ o
 // decode: same tiling; `out` must be 16-byte aligned when ntiles > 0.  Tiles cover only words whose 27
 // nucleotides are all wanted (27*128*ntiles <= len); the scalar warp writes the rest up to len.
 // ------------------------------------------------------------------------------------------------------
+template <bool TMA>
 __global__ void __launch_bounds__(kB5Warps * 32)
 b5_decode_kernel(const uint64_t *__restrict__ bits, uint8_t *__restrict__ out, size_t len, size_t ntiles, size_t total_words)
 {
-    __shared__ __align__(16) uint8_t smem[kB5Warps * kB5SmemPerWarp];
+    __shared__ __align__(128) uint8_t smem[kB5Warps * kB5SmemPerWarp];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t g = (size_t)blockIdx.x * kB5Warps + warp;
     if (g < ntiles) {
         uint8_t *tile = smem + warp * kB5SmemPerWarp;
         uint32_t *tw = reinterpret_cast<uint32_t *>(tile);
         const uint64_t *src = bits + g * kB5WarpWords;
-        uint2 w[4];
+        const u32x8 w = ld_stream32(src + 4 * lane);                 // this lane's 4 words
+        uint32_t a[4][7];
 #pragma unroll
-        for (int c = 0; c < 4; c++) w[c] = ld_stream8(src + lane + 32 * c);
-        const unsigned own = lane & 3u;                         // = (-27*lane) mod 4: bytes until the lane's first owned word
+        for (int c = 0; c < 4; c++) b5_unpack27(make_uint2(w.v[2 * c], w.v[2 * c + 1]), a[c]);
+        uint32_t o[27];
+        b5_splice108(a, o);
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            uint32_t a[8];
-            {
-                uint32_t s[7];
-                b5_unpack27(w[c], s);
-#pragma unroll
-                for (int k = 0; k < 7; k++) a[k] = s[k];
-            }
-            // a lane owns the smem words that START inside its 27 bytes; the last of them also holds the first
-            // bytes of the next lane's group, fetched with one shuffle (lane 31 owns none of those: own == 3)
-            uint32_t next = __shfl_down_sync(0xFFFFFFFFu, a[0], 1);
-            a[6] = __byte_perm(a[6], next, 0x4210);             // bytes 24,25,26 + neighbour byte 0
-            a[7] = next >> 8;                                   // neighbour bytes 1,2,3
-            const unsigned w0 = (kB5Nt * (lane + 32 * c) + own) >> 2;
+        for (int k = 0; k < 27; k++) tw[27 * lane + k] = o[k];
+        uint8_t *dst = out + g * kB5WarpBytes;
+        if constexpr (TMA) {
+            fence_proxy_async_smem();                           // generic-proxy writes -> visible to the async proxy
+            __syncwarp();
+            if (lane == 0) { bulk_store(dst, tile, kB5WarpBytes); bulk_store_wait_read(); }
+        } else {
+            __syncwarp();
 #pragma unroll
             for (int k = 0; k < 7; k++) {
-                uint32_t word = __funnelshift_r(a[k], a[k + 1], 8 * own);
-                if (k < 6 || own != 3) tw[w0 + k] = word;
+                unsigned i = lane + 32 * k;
+                if (i < kB5WarpVecs) st_stream16(dst + 16 * i, *reinterpret_cast<const uint4 *>(tile + 16 * i));
             }
-        }
-        __syncwarp();
-        uint8_t *dst = out + g * kB5WarpBytes;
-#pragma unroll
-        for (int k = 0; k < 7; k++) {
-            unsigned i = lane + 32 * k;
-            if (i < kB5WarpVecs) st_stream16(dst + 16 * i, *reinterpret_cast<const uint4 *>(tile + 16 * i));
         }
     } else if (g == ntiles) {
         b5_decode_scalar(bits, out, len, ntiles * kB5WarpWords, total_words, lane, 32);
