@@ -231,13 +231,25 @@ def run_gpu(args, rank, local_rank, world):
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
-    L = args.nucleotides
+    from cute_nucleotides_b200 import sharded
+    strong = args.total_gib > 0
+    if strong:
+        total = int(args.total_gib * GIB)
+        offset, end = sharded.shard_bounds(total, world, rank, 1 << 20)
+        L = end - offset
+    else:
+        L = args.nucleotides
+        offset = rank * L                                # shard by sequence offset of one logical N*L sequence
     W = cn.words_for_len(L)
-    offset = rank * L                                    # shard by sequence offset of one logical N*L sequence
     d_n = torch.empty(L, dtype=torch.uint8, device=dev)
     d_bits = torch.empty(W, dtype=torch.int64, device=dev)
-    d_out = torch.empty(L, dtype=torch.uint8, device=dev)
+    free_b, _ = torch.cuda.mem_get_info(dev)
+    in_place = free_b < L + (8 << 30)                    # SURVEY 7 hard part 4: 80 GiB + 20 GiB + 80 GiB > one B200
+    d_out = d_n if in_place else torch.empty(L, dtype=torch.uint8, device=dev)
     cn.generate_device(d_n, offset, SEED, args.alphabet)
+    if in_place:                                         # the round trip then maps the buffer onto its canonical form:
+        cn.encode_device(d_n, out=d_bits)                # start from the canonical form so every step does the same work
+        cn.decode_device(d_bits, L, out=d_n)
     stream = torch.cuda.current_stream()
 
     def step():
@@ -275,7 +287,7 @@ def run_gpu(args, rank, local_rank, world):
     ms_per_step = total_ms / K
 
     # ---- verification (outside the timed region): the timed outputs are bit-exact ---------------------
-    verified = verify(cn, torch, np, d_n, d_bits, d_out, L, offset, args.alphabet)
+    verified = verify(cn, torch, np, d_n, d_bits, d_out, L, offset, args.alphabet, in_place)
 
     # ---- optional assemble of the packed shards (the only collective the path can use; not in `value`)
     assemble = None
@@ -311,6 +323,7 @@ def run_gpu(args, rank, local_rank, world):
 
     if rank != 0:
         return
+    total_nt = int(args.total_gib * GIB) if strong else world * L
     peak, peak_src = measured_peak()
     dom = "decode" if dec_avg >= enc_avg else "encode"
     dom_ms = max(dec_avg, enc_avg)
@@ -323,16 +336,19 @@ def run_gpu(args, rank, local_rank, world):
         lib.cn_get_tuning(d, ctypes.byref(vec), ctypes.byref(unroll), ctypes.byref(threads))
         tuning[name] = {"vec_bytes": vec.value, "unroll": unroll.value, "threads": threads.value}
     line = {
-        "metric": METRIC, "value": world * L / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": total_nt / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": workload_name(args), "nucleotides_per_gpu": L, "alphabet": args.alphabet, "seed": SEED,
+        "config": {"workload": workload_name(args) if not strong else f"{args.total_gib:g} GiB random sequence sharded by offset over {world} GPU(s): encode then decode (BASELINE config 5)",
+                   "nucleotides_per_gpu": L, "decode_in_place": bool(in_place), "alphabet": args.alphabet, "seed": SEED,
                    "sharding": "contiguous by sequence offset, one shard per rank, no data-path collective",
                    "l2": "inputs (>= 2.5 GiB per kernel) exceed the 126 MB L2; no flush needed", "tuning": tuning},
-        "encode_nt_per_s": world * L / (enc_avg * 1e-3), "decode_nt_per_s": world * L / (dec_avg * 1e-3),
+        "encode_nt_per_s": total_nt / (enc_avg * 1e-3), "decode_nt_per_s": total_nt / (dec_avg * 1e-3),
         "encode_ms": enc_avg, "decode_ms": dec_avg,
         "roofline": {"bound": "hbm", "kernel": f"{dom}_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": (traffic or {}).get(dom), "peak_source": peak_src,
+                     "frac": achieved / peak,
+                     "traffic": (traffic or {}).get(dom) if L == 10 * GIB else None,   # the ncu capture is of 10 GiB launches
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": BYTES_PER_NT * L,
                      "encode": {"achieved": BYTES_PER_NT * L / (enc_avg * 1e-3) / 1e9, "frac": BYTES_PER_NT * L / (enc_avg * 1e-3) / 1e9 / peak},
                      "decode": {"achieved": BYTES_PER_NT * L / (dec_avg * 1e-3) / 1e9, "frac": BYTES_PER_NT * L / (dec_avg * 1e-3) / 1e9 / peak}},
@@ -347,7 +363,7 @@ def run_gpu(args, rank, local_rank, world):
     print(json.dumps(line), flush=True)
 
 
-def verify(cn, torch, np, d_n, d_bits, d_out, L, offset, alphabet):
+def verify(cn, torch, np, d_n, d_bits, d_out, L, offset, alphabet, in_place=False):
     """decode(encode(x)) == canonical(x) over a 256 MiB prefix and the ragged end (device side), and a
     4 MiB window of packed words bit-exact against the oracle's n_to_bits_lut of the host-generated data."""
     import _oracle
@@ -358,7 +374,11 @@ def verify(cn, torch, np, d_n, d_bits, d_out, L, offset, alphabet):
     ok = True
     span = min(L, 1 << 28)
     for s in (0, L - span):
-        ok &= bool(torch.equal(d_out[s:s + span], lut[d_n[s:s + span].long()]))
+        if in_place:        # d_n was overwritten by its canonical form: compare against the regenerated input
+            fresh = cn.generate_device(torch.empty(span, dtype=torch.uint8, device=d_n.device), offset + s, SEED, alphabet)
+            ok &= bool(torch.equal(d_out[s:s + span], lut[fresh.long()]))
+        else:
+            ok &= bool(torch.equal(d_out[s:s + span], lut[d_n[s:s + span].long()]))
     win = min(L, 1 << 22)
     for s in (0, ((L - win) // 2) & ~31, (L - win) & ~31):
         host = orc.generate(min(win, L - s), SEED, alphabet, offset=offset + s)
@@ -441,6 +461,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nucleotides", type=int, default=10 * GIB, help="nucleotides per GPU per step (default 10 GiB)")
+    ap.add_argument("--total-gib", type=float, default=0.0,
+                    help="strong scaling (BASELINE config 5): shard this many GiB of ONE sequence over the ranks instead of "
+                         "10 GiB per rank; decode writes back over the input when two ASCII buffers do not fit")
     ap.add_argument("--alphabet", type=int, default=10, choices=[4, 10])
     ap.add_argument("--e2e-nucleotides", type=int, default=0, help="e2e batch (default: same as --nucleotides)")
     ap.add_argument("--e2e-steps", type=int, default=3)

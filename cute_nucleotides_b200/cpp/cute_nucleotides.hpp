@@ -70,4 +70,33 @@ template <class A> inline Bytes bits_to_n_cuda(const std::vector<uint64_t, A> &b
 }
 
 }  // namespace n_to_bits
+
+// Mirror of `cute_nucleotides::n_to_bits2` (src/n_to_bits2.rs): {A, C, T/U, G, N}, 27 nucleotides per u64.
+namespace n_to_bits2 {
+using n_to_bits::Bytes;
+using n_to_bits::Words;
+using n_to_bits::check_status;
+
+/// Mirrors n_to_bits2_lut (src/n_to_bits2.rs:37).
+inline Words n_to_bits2_cuda(const uint8_t *n, size_t len)
+{
+    Words res(cn_words2_for_len(len));
+    check_status(cn_n_to_bits2_host(n, len, res.data()));
+    return res;
+}
+inline Words n_to_bits2_cuda(std::string_view n) { return n_to_bits2_cuda(reinterpret_cast<const uint8_t *>(n.data()), n.size()); }
+
+/// Mirrors bits_to_n2_lut (src/n_to_bits2.rs:78): throws std::length_error if len > 27 * nwords (:79-81).
+inline Bytes bits_to_n2_cuda(const uint64_t *bits, size_t nwords, size_t len)
+{
+    if (len > nwords * 27) throw std::length_error(cn_length_panic_message());
+    Bytes res(len);
+    check_status(cn_bits_to_n2_host(bits, nwords, len, res.data()));
+    return res;
+}
+template <class A> inline Bytes bits_to_n2_cuda(const std::vector<uint64_t, A> &bits, size_t len)
+{
+    return bits_to_n2_cuda(bits.data(), bits.size(), len);
+}
+}  // namespace n_to_bits2
 }  // namespace cute_nucleotides

@@ -17,6 +17,7 @@
 #include "../cute_nucleotides_b200/cpp/cute_nucleotides.hpp"
 
 using namespace cute_nucleotides::n_to_bits;
+using namespace cute_nucleotides::n_to_bits2;
 
 static int g_failed = 0;
 template <class A, class B> static bool same(const A &a, const B &b)
@@ -92,6 +93,36 @@ static void test_unaligned_slice()
     }
 }
 
+static void test_n_to_bits2_cuda()
+{   // src/n_to_bits2.rs:275-279 (and :289-293)
+    ASSERT_EQ(n_to_bits2_cuda("ATCGNATCGNATCGNATCGNATCGNATCGNATCGN"),
+              (std::vector<uint64_t>{0b11011010100100010111010001111101000110110101001000101110100011ull, 0b1011101000111110100ull}));
+    ASSERT_EQ(n_to_bits2_cuda("ATCGN"), (std::vector<uint64_t>{0b101110100011ull}));
+}
+
+static void test_bits_to_n2_cuda()
+{   // src/n_to_bits2.rs:282-286 (and :296-298)
+    ASSERT_EQ(bits_to_n2_cuda(std::vector<uint64_t>{0b11011010100100010111010001111101000110110101001000101110100011ull, 0b1011101000111110100ull}, 35),
+              bytes("ATCGNATCGNATCGNATCGNATCGNATCGNATCGN"));
+    bool thrown = false;
+    try { bits_to_n2_cuda(std::vector<uint64_t>{0, 0}, 55); }
+    catch (const std::length_error &e) { thrown = std::string(e.what()) == "The length is greater than the number of nucleotides!"; }
+    ASSERT_EQ(thrown, true);
+}
+
+static void test_base5_round_trip_lengths()
+{
+    const std::string unit = "GATTACANgattacanUuCcGgAaTtNn";
+    for (size_t len : {0, 1, 2, 26, 27, 28, 55, 3456, 3457, 40000, 100003}) {
+        std::string s = repeat(unit, len / unit.size() + 1).substr(0, len);
+        auto w = n_to_bits2_cuda(s);
+        ASSERT_EQ(w.size(), (len + 26) / 27);
+        std::string canon = s;
+        for (auto &c : canon) { c = (char)std::toupper((unsigned char)c); if (c == 'U') c = 'T'; }
+        ASSERT_EQ(bits_to_n2_cuda(w, len), bytes(canon));
+    }
+}
+
 template <typename F> static double median_seconds(F f, int min_iters, double min_total)
 {
     std::vector<double> t;
@@ -135,7 +166,10 @@ int main(int argc, char **argv)
             test_body_and_tail_lengths();
             test_length_panic();
             test_unaligned_slice();
-            std::printf(g_failed ? "test result: FAILED. %d failed\n" : "test result: ok. 6 passed; %d failed\n", g_failed);
+            test_n_to_bits2_cuda();
+            test_bits_to_n2_cuda();
+            test_base5_round_trip_lengths();
+            std::printf(g_failed ? "test result: FAILED. %d failed\n" : "test result: ok. 9 passed; %d failed\n", g_failed);
             return g_failed ? 1 : 0;
         }
         if (mode == "bench") {
