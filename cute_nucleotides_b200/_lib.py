@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcute_nucleotides_cuda.so")
+LIB_PATH = os.environ.get("CN_CUDA_LIB", os.path.join(_HERE, "libcute_nucleotides_cuda.so"))   # override: A/B builds only
 
 CN_OK, CN_ERR_LENGTH, CN_ERR_CUDA, CN_ERR_ARG, CN_ERR_NOMEM = 0, 1, 2, 3, 4
 CN_DIR_ENCODE, CN_DIR_DECODE = 0, 1
@@ -29,6 +29,8 @@ PROTOTYPES = {
     "cn_bits_to_n_host": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p]),
     "cn_encode_device": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "cn_decode_device": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
+    "cn_n_to_bits_checked_host": (c_int, [c_void_p, c_size_t, c_void_p, POINTER(c_uint64)]),
+    "cn_encode_checked_device": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "cn_words2_for_len": (c_size_t, [c_size_t]),
     "cn_n_to_bits2_host": (c_int, [c_void_p, c_size_t, c_void_p]),
     "cn_bits_to_n2_host": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p]),

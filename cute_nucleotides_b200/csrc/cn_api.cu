@@ -88,7 +88,7 @@ cudaError_t enc_launch(const EncArgs &a, cudaStream_t s)
     if (blocks == 0) blocks = 1;                       // the ragged end still needs its warp
     if (blocks > kMaxGrid) return cudaErrorInvalidConfiguration;
     cn::encode_kernel<VEC, U, T, MIS><<<(unsigned)blocks, T, 0, s>>>(a.in, a.out32, a.nvec, a.n0, a.len,
-                                                                    a.edge_first, a.edge_total, a.shift_bytes);
+                                                                    a.edge_first, a.edge_total, a.shift_bytes, nullptr);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
@@ -178,6 +178,57 @@ int encode_device(const void *d_n, size_t len, void *d_out, cudaStream_t s)
         e = enc_launch<16, 4, 256, true>(a, s);
     }
     if (e != cudaSuccess) return fail(CN_ERR_CUDA, "encode kernel launch failed: %s", cudaGetErrorString(e));
+    return CN_OK;
+}
+
+// encode + validation in one pass (fixed launch shapes: the measured-best ones)
+template <int VEC, int U, int T, bool MIS>
+cudaError_t enc_launch_checked(const EncArgs &a, unsigned long long *counter, cudaStream_t s)
+{
+    size_t tile = (size_t)U * T;
+    size_t blocks = (a.nvec + tile - 1) / tile;
+    if (blocks == 0) blocks = 1;
+    if (blocks > kMaxGrid) return cudaErrorInvalidConfiguration;
+    cn::encode_kernel<VEC, U, T, MIS, true><<<(unsigned)blocks, T, 0, s>>>(a.in, a.out32, a.nvec, a.n0, a.len,
+                                                                          a.edge_first, a.edge_total, a.shift_bytes, counter);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+int encode_checked_device(const void *d_n, size_t len, void *d_out, void *d_invalid, cudaStream_t s)
+{
+    if (!d_invalid || (addr(d_invalid) & 7)) return fail(CN_ERR_ARG, "cn_encode_checked_device: counter must be a non-null 8-byte aligned device pointer");
+    if (len == 0) return CN_OK;
+    if (!d_n || !d_out) return fail(CN_ERR_ARG, "cn_encode_checked_device: null pointer");
+    if (addr(d_out) & 7) return fail(CN_ERR_ARG, "cn_encode_checked_device: output must be 8-byte aligned");
+    unsigned long long *counter = static_cast<unsigned long long *>(d_invalid);
+    EncArgs a{};
+    a.n0 = static_cast<const uint8_t *>(d_n);
+    a.len = len;
+    a.out32 = static_cast<uint32_t *>(d_out);
+    a.edge_total = cn_words_for_len(len) * 2;
+    cudaError_t e;
+    const unsigned mis = (unsigned)(addr(d_n) & 15);
+    if (mis == 0) {
+        a.in = a.n0;
+        if ((addr(d_n) & 31) == 0) {
+            a.nvec = len >> 5;
+            a.edge_first = a.nvec * 2;
+            e = enc_launch_checked<32, 1, 256, false>(a, counter, s);
+        } else {
+            a.nvec = len >> 4;
+            a.edge_first = a.nvec;
+            e = enc_launch_checked<16, 2, 256, false>(a, counter, s);
+        }
+    } else {
+        size_t spans = (len + mis) >> 4;
+        a.in = a.n0 - mis;
+        a.shift_bytes = mis;
+        a.nvec = spans > 0 ? spans - 1 : 0;
+        a.edge_first = a.nvec;
+        e = enc_launch_checked<16, 4, 256, true>(a, counter, s);
+    }
+    if (e != cudaSuccess) return fail(CN_ERR_CUDA, "checked encode kernel launch failed: %s", cudaGetErrorString(e));
     return CN_OK;
 }
 
@@ -391,6 +442,7 @@ struct HostPipe {
     int device = -1;
     size_t chunk = 0;
     Slot slot[kSlots];
+    unsigned long long *d_counter = nullptr;              // invalid-byte counter of the checked encode
     bool ready = false;
 
     void destroy()
@@ -404,9 +456,13 @@ struct HostPipe {
             if (sl.stream) cudaStreamDestroy(sl.stream);
             sl = Slot{};
         }
+        if (d_counter) cudaFree(d_counter);
+        d_counter = nullptr;
         ready = false;
     }
-    ~HostPipe() { /* process teardown: the driver reclaims everything; avoid calls after unload */ }
+    // A thread that used the host-slice calls releases its staging when it exits (thread_local destructors of a
+    // live process run while the CUDA runtime is still loaded; failures during teardown are ignored).
+    ~HostPipe() { if (ready) { destroy(); cudaGetLastError(); } }
 };
 
 thread_local HostPipe t_pipe;
@@ -433,6 +489,11 @@ int pipe_prepare(HostPipe &p)
             return fail(CN_ERR_NOMEM, "host pipeline: staging allocation of %zu bytes per slot failed", p.chunk);
         }
     }
+    if (cudaMalloc(&p.d_counter, sizeof(unsigned long long)) != cudaSuccess) {
+        cudaGetLastError();
+        p.destroy();
+        return fail(CN_ERR_NOMEM, "host pipeline: counter allocation failed");
+    }
     p.ready = true;
     return CN_OK;
 }
@@ -453,7 +514,7 @@ bool is_pinned(const void *p, size_t bytes)
 // One implementation for both directions and both codecs: `big` is the ASCII side, `small` the packed side.
 //   encode: src = ASCII (len bytes)          dst = packed (8*words bytes)
 //   decode: src = packed (8*nwords bytes)    dst = ASCII (len bytes)
-int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, size_t len)
+int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, size_t len, uint64_t *invalid_out = nullptr)
 {
     HostPipe &p = t_pipe;
     int rc = pipe_prepare(p);
@@ -465,6 +526,19 @@ int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, s
     // Staging holds p.chunk ASCII bytes and p.chunk/4 (+64) packed bytes per slot; the base-5 codec packs
     // 8 bytes per 27 nucleotides (> 1/4), so its chunks are 3/4 of the staging size.
     const size_t max_nt = cd.group == 32 ? p.chunk : p.chunk / 4 * 3;
+    // checked encode (2-bit codec only): every chunk's kernel adds into one device counter, read back at the end
+    const bool checked = invalid_out != nullptr;
+    auto run_encode = [&](const void *in, size_t nt, void *out, cudaStream_t s) {
+        return checked ? encode_checked_device(in, nt, out, p.d_counter, s) : cd.enc(in, nt, out, s);
+    };
+    auto finish_checked = [&]() -> int {
+        if (!checked) return CN_OK;
+        unsigned long long v = 0;
+        CN_CUDA(cudaMemcpy(&v, p.d_counter, sizeof v, cudaMemcpyDeviceToHost));
+        *invalid_out = v;
+        return CN_OK;
+    };
+    if (checked) CN_CUDA(cudaMemset(p.d_counter, 0, sizeof(unsigned long long)));
 
     // Small inputs (the reference's own bench is 40 000 nt) are latency-bound: skip the pointer queries and
     // the copy engines, stage through slot 0's pinned buffers and let ONE kernel read and write them in place
@@ -474,11 +548,11 @@ int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, s
         uint8_t *pin_in = encode ? sl.pin_big : sl.pin_small;
         uint8_t *pin_out = encode ? sl.pin_small : sl.pin_big;
         memcpy(pin_in, src, src_bytes);
-        rc = encode ? cd.enc(pin_in, len, pin_out, sl.stream) : cd.dec(pin_in, nwords, len, pin_out, sl.stream);
+        rc = encode ? run_encode(pin_in, len, pin_out, sl.stream) : cd.dec(pin_in, nwords, len, pin_out, sl.stream);
         if (rc != CN_OK) return rc;
         CN_CUDA(cudaStreamSynchronize(sl.stream));
         memcpy(dst, pin_out, dst_bytes);
-        return CN_OK;
+        return finish_checked();
     }
 
     const bool src_pinned = is_pinned(src, src_bytes);
@@ -488,10 +562,10 @@ int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, s
     // zero-copy with both sides page-locked: a single kernel streams over PCIe in both directions
     if (zero_copy && src_pinned && dst_pinned) {
         cudaStream_t s = p.slot[0].stream;
-        rc = encode ? cd.enc(src, len, dst, s) : cd.dec(src, nwords, len, dst, s);
+        rc = encode ? run_encode(src, len, dst, s) : cd.dec(src, nwords, len, dst, s);
         if (rc != CN_OK) return rc;
         CN_CUDA(cudaStreamSynchronize(s));
-        return CN_OK;
+        return finish_checked();
     }
 
     // Nucleotides per chunk: a multiple of `unit` (whole words, and whole warp tiles / 16-byte vectors where the
@@ -541,10 +615,10 @@ int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, s
 
         if (zero_copy) {
             // kernel dereferences the pinned staging (or the caller's pinned side) directly
-            rc = encode ? cd.enc(h_in, nt, h_out, sl.stream) : cd.dec(h_in, words, nt, h_out, sl.stream);
+            rc = encode ? run_encode(h_in, nt, h_out, sl.stream) : cd.dec(h_in, words, nt, h_out, sl.stream);
         } else {
             CN_CUDA(cudaMemcpyAsync(dev_in, h_in, in_bytes, cudaMemcpyHostToDevice, sl.stream));
-            rc = encode ? cd.enc(dev_in, nt, dev_out, sl.stream) : cd.dec(dev_in, words, nt, dev_out, sl.stream);
+            rc = encode ? run_encode(dev_in, nt, dev_out, sl.stream) : cd.dec(dev_in, words, nt, dev_out, sl.stream);
             if (rc == CN_OK) CN_CUDA(cudaMemcpyAsync(h_out, dev_out, out_bytes, cudaMemcpyDeviceToHost, sl.stream));
         }
         if (rc != CN_OK) { first_error = rc; break; }
@@ -565,6 +639,7 @@ int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, s
         if (e == cudaSuccess && sl.dst_bytes) staged_copy(dst + sl.dst_off, encode ? sl.pin_small : sl.pin_big, sl.dst_bytes);
         sl.busy = false;
     }
+    if (first_error == CN_OK) first_error = finish_checked();
     return first_error;
 }
 
@@ -629,6 +704,20 @@ int cn_bits_to_n_host(const uint64_t *bits, size_t nwords, size_t len, uint8_t *
     if (len == 0) return CN_OK;
     if (!bits || !out) return fail(CN_ERR_ARG, "cn_bits_to_n_host: null pointer");
     return host_codec(kCodec2bit, false, reinterpret_cast<const uint8_t *>(bits), out, len);
+}
+
+int cn_n_to_bits_checked_host(const uint8_t *n, size_t len, uint64_t *out, uint64_t *invalid_count)
+{
+    if (!invalid_count) return fail(CN_ERR_ARG, "cn_n_to_bits_checked_host: null counter");
+    *invalid_count = 0;
+    if (len == 0) return CN_OK;
+    if (!n || !out) return fail(CN_ERR_ARG, "cn_n_to_bits_checked_host: null pointer");
+    return host_codec(kCodec2bit, true, n, reinterpret_cast<uint8_t *>(out), len, invalid_count);
+}
+
+int cn_encode_checked_device(const void *d_n, size_t len, void *d_out, void *d_invalid_count, void *stream)
+{
+    return encode_checked_device(d_n, len, d_out, d_invalid_count, static_cast<cudaStream_t>(stream));
 }
 
 int cn_encode_device(const void *d_n, size_t len, void *d_out, void *stream)

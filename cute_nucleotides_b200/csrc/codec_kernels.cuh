@@ -35,6 +35,22 @@ constexpr uint32_t kAsciiCodeMask = 0x06060606u;                                
 constexpr uint32_t kPackMul = (1u << 23) | (1u << 17) | (1u << 11) | (1u << 5);    // 0x00820820
 constexpr uint32_t kLutWord = 0x47544341u;                                         // 'A','C','T','G'
 
+// PRMT with a run-time selector.  __byte_perm() ANDs a variable selector with 0x7777 (an extra LOP3 per use);
+// every selector built in this file already has nibbles <= 7, so the raw instruction is used instead.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+// (a & mask) | (b & ~mask) in ONE LOP3 (immLut 0xE4 = c ? a : b); nvcc splits the two-constant form into two.
+__device__ __forceinline__ uint32_t bitselect(uint32_t a, uint32_t b, uint32_t mask)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(mask));
+    return d;
+}
+
 // 4 ASCII bytes -> their 4 codes in the TOP byte of the result (lower bytes are garbage)
 __device__ __forceinline__ uint32_t pack4_top(uint32_t x) { return (x & kAsciiCodeMask) * kPackMul; }
 
@@ -54,8 +70,8 @@ __device__ __forceinline__ void unpack8(uint32_t w, uint32_t &a, uint32_t &b)
     uint32_t s = __byte_perm(w, 0u, kHigh ? 0x4342 : 0x4140);   // [b, 0, b', 0]
     s = (s | (s << 4)) & 0x0F0F0F0Fu;
     s = (s | (s << 2)) & 0x33333333u;                           // nibble k = code k
-    a = __byte_perm(kLutWord, 0u, s);                           // PRMT reads the low 16 selector bits
-    b = __byte_perm(kLutWord, 0u, s >> 16);
+    a = prmt(kLutWord, 0u, s);                                  // PRMT reads the low 16 selector bits
+    b = prmt(kLutWord, 0u, s >> 16);
 }
 
 // 16 codes (one u32 of the packed stream) -> 16 ASCII bytes
@@ -65,6 +81,39 @@ __device__ __forceinline__ uint4 unpack16(uint32_t w)
     unpack8<false>(w, r.x, r.y);
     unpack8<true>(w, r.z, r.w);
     return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// validation fused into the encode pass (optional): which bytes are outside {A,C,G,T,U,a,c,g,t,u}?
+// A byte is valid iff b & 0xD8 (everything but the case bit and the low 3 bits) equals what its low 3 bits
+// predict: a/c/g (index 1,3,7) -> 0x40, t/u (index 4,5) -> 0x50; indices 0,2,6 can never match.  Per 32-bit register: pack the four 3-bit indices
+// into PRMT selector nibbles (the shift runs on the FMA pipe as a multiply-high), one PRMT to pack, one PRMT
+// lookup, one LOP3 for the masked byte, one LOP3 to XOR and OR-accumulate: 5 ALU-pipe ops per 4 nucleotides.
+// Bit 3 / bit 7 of a byte leak into selector nibbles as PRMT's sign-replicate flag; that can only turn a
+// match into a mismatch next to a byte that is itself invalid, so the accumulated word is an exact
+// "anything invalid?" flag, and a thread that sees it set recounts its bytes one by one.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t invalid_accumulate(uint32_t acc, uint32_t x)
+{
+    uint32_t t = bitselect(x, __umulhi(x, 0x10000000u), 0x8F8F8F8Fu);     // byte0 = n0 | i1<<4, byte2 = n2 | i3<<4
+    uint32_t expect = prmt(0x40FF40FFu, 0x40FF5050u, __byte_perm(t, 0u, 0x4420));
+    return acc | ((x & 0xD8D8D8D8u) ^ expect);                            // non-zero <=> some byte is invalid
+}
+__device__ __forceinline__ bool invalid_byte(uint32_t b)
+{
+    uint32_t c = b | 0x20u;
+    return !(c == 'a' || c == 'c' || c == 'g' || c == 't' || c == 'u');
+}
+__device__ __forceinline__ uint32_t count_invalid4(uint32_t x)
+{
+    return (uint32_t)invalid_byte(x & 0xFFu) + (uint32_t)invalid_byte((x >> 8) & 0xFFu) +
+           (uint32_t)invalid_byte((x >> 16) & 0xFFu) + (uint32_t)invalid_byte(x >> 24);
+}
+// one atomic per warp, and only when something was invalid
+__device__ __forceinline__ void report_invalid(unsigned long long *counter, uint32_t mine)
+{
+    uint32_t total = __reduce_add_sync(0xFFFFFFFFu, mine);
+    if (total && (threadIdx.x & 31) == 0) atomicAdd(counter, (unsigned long long)total);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -124,9 +173,10 @@ __device__ __forceinline__ void st_stream32(void *p, const uint4 &a, const uint4
 
 // encode u32 units [first, total): unit u covers nucleotides 16u..16u+15, zero-padded beyond len
 // (the zero padding is the "unused high bits of the last word are zero" rule, n_to_bits.rs:35).
-__device__ __forceinline__ void encode_edge(const uint8_t *__restrict__ n, size_t len,
-                                            uint32_t *__restrict__ out32, size_t first, size_t total, unsigned lane)
+__device__ __forceinline__ uint32_t encode_edge(const uint8_t *__restrict__ n, size_t len,
+                                                uint32_t *__restrict__ out32, size_t first, size_t total, unsigned lane)
 {
+    uint32_t invalid = 0;
     for (size_t u = first + lane; u < total; u += 32) {
         uint32_t code = 0;
         size_t base = u << 4;
@@ -135,9 +185,11 @@ __device__ __forceinline__ void encode_edge(const uint8_t *__restrict__ n, size_
             size_t i = base + k;
             uint32_t byte = (i < len) ? (uint32_t)n[i] : 0u;      // 0 -> code 0
             code |= ((byte >> 1) & 3u) << (2 * k);
+            if (i < len && invalid_byte(byte)) invalid++;
         }
         out32[u] = code;
     }
+    return invalid;                                               // bytes outside the alphabet among those this lane read
 }
 
 // decode nucleotides [from, len) with byte stores; bits32 is the packed stream viewed as u32
@@ -159,15 +211,24 @@ __device__ __forceinline__ void decode_edge(const uint32_t *__restrict__ bits32,
 //   nvec    : number of full VEC-byte groups the body covers
 //   edge_*  : the warp-sized ragged end, run by the last warp of the last CTA
 // ------------------------------------------------------------------------------------------------
-template <int VEC, int UNROLL, int THREADS, bool MISALIGN>
+template <int VEC, int UNROLL, int THREADS, bool MISALIGN, bool CHECK = false>
 __global__ void __launch_bounds__(THREADS)
 encode_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out32, size_t nvec,
-              const uint8_t *__restrict__ n0, size_t len, size_t edge_first, size_t edge_total, unsigned shift_bytes)
+              const uint8_t *__restrict__ n0, size_t len, size_t edge_first, size_t edge_total, unsigned shift_bytes,
+              unsigned long long *__restrict__ invalid_counter)
 {
     static_assert(VEC == 16 || VEC == 32, "VEC");
     constexpr size_t kTile = (size_t)THREADS * UNROLL;
     const size_t tile0 = (size_t)blockIdx.x * kTile;
     const size_t t = tile0 + threadIdx.x;
+    uint32_t n_invalid = 0;                // bytes outside the alphabet seen by this thread (CHECK, and the edge warp)
+    // CHECK: validate the registers that were just encoded; the exact count is only taken on a mismatch
+    auto check16 = [&](uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+        if constexpr (CHECK) {
+            uint32_t bad = invalid_accumulate(invalid_accumulate(invalid_accumulate(invalid_accumulate(0u, a), b), c), d);
+            if (bad) n_invalid += count_invalid4(a) + count_invalid4(b) + count_invalid4(c) + count_invalid4(d);
+        }
+    };
 
     if constexpr (!MISALIGN) {
         if (tile0 + kTile <= nvec) {                      // full tile: no bounds checks
@@ -176,16 +237,22 @@ encode_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out32, size
 #pragma unroll
                 for (int u = 0; u < UNROLL; u++) v[u] = ld_stream16(in + ((t + (size_t)u * THREADS) << 4));
 #pragma unroll
-                for (int u = 0; u < UNROLL; u++) st_stream4(out32 + t + (size_t)u * THREADS, pack16(v[u]));
+                for (int u = 0; u < UNROLL; u++) {
+                    st_stream4(out32 + t + (size_t)u * THREADS, pack16(v[u]));
+                    check16(v[u].x, v[u].y, v[u].z, v[u].w);
+                }
             } else {
                 u32x8 v[UNROLL];
 #pragma unroll
                 for (int u = 0; u < UNROLL; u++) v[u] = ld_stream32(in + ((t + (size_t)u * THREADS) << 5));
 #pragma unroll
-                for (int u = 0; u < UNROLL; u++)
+                for (int u = 0; u < UNROLL; u++) {
                     st_stream8(out32 + ((t + (size_t)u * THREADS) << 1),
                                pack16(v[u].v[0], v[u].v[1], v[u].v[2], v[u].v[3]),
                                pack16(v[u].v[4], v[u].v[5], v[u].v[6], v[u].v[7]));
+                    check16(v[u].v[0], v[u].v[1], v[u].v[2], v[u].v[3]);
+                    check16(v[u].v[4], v[u].v[5], v[u].v[6], v[u].v[7]);
+                }
             }
         } else {
 #pragma unroll
@@ -193,11 +260,15 @@ encode_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out32, size
                 size_t i = t + (size_t)u * THREADS;
                 if (i < nvec) {
                     if constexpr (VEC == 16) {
-                        st_stream4(out32 + i, pack16(ld_stream16(in + (i << 4))));
+                        uint4 v = ld_stream16(in + (i << 4));
+                        st_stream4(out32 + i, pack16(v));
+                        check16(v.x, v.y, v.z, v.w);
                     } else {
                         u32x8 v = ld_stream32(in + (i << 5));
                         st_stream8(out32 + (i << 1), pack16(v.v[0], v.v[1], v.v[2], v.v[3]),
                                    pack16(v.v[4], v.v[5], v.v[6], v.v[7]));
+                        check16(v.v[0], v.v[1], v.v[2], v.v[3]);
+                        check16(v.v[4], v.v[5], v.v[6], v.v[7]);
                     }
                 }
             }
@@ -223,14 +294,17 @@ encode_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out32, size
                     if (word_off == 3) s = w[k + 3];
                     x[k] = s;
                 }
-                st_stream4(out32 + i, pack16(__funnelshift_r(x[0], x[1], bit_off), __funnelshift_r(x[1], x[2], bit_off),
-                                             __funnelshift_r(x[2], x[3], bit_off), __funnelshift_r(x[3], x[4], bit_off)));
+                const uint32_t y0 = __funnelshift_r(x[0], x[1], bit_off), y1 = __funnelshift_r(x[1], x[2], bit_off),
+                               y2 = __funnelshift_r(x[2], x[3], bit_off), y3 = __funnelshift_r(x[3], x[4], bit_off);
+                st_stream4(out32 + i, pack16(y0, y1, y2, y3));
+                check16(y0, y1, y2, y3);
             }
         }
     }
 
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x >= THREADS - 32)
-        encode_edge(n0, len, out32, edge_first, edge_total, threadIdx.x & 31);
+        n_invalid += encode_edge(n0, len, out32, edge_first, edge_total, threadIdx.x & 31);
+    if constexpr (CHECK) report_invalid(invalid_counter, n_invalid);
 }
 
 // ------------------------------------------------------------------------------------------------

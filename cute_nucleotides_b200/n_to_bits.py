@@ -20,7 +20,7 @@ from . import _lib
 from ._lib import LengthError, check
 
 __all__ = [
-    "n_to_bits_cuda", "bits_to_n_cuda", "words_for_len",
+    "n_to_bits_cuda", "bits_to_n_cuda", "words_for_len", "n_to_bits_checked_cuda", "encode_checked_device",
     "encode_device", "decode_device", "generate_device", "generate_words_device", "LengthError",
 ]
 
@@ -45,6 +45,16 @@ def n_to_bits_cuda(n) -> np.ndarray:
     if src.size:
         check(_lib.load().cn_n_to_bits_host(src.ctypes.data, src.size, out.ctypes.data))
     return out
+
+
+def n_to_bits_checked_cuda(n):
+    """Like n_to_bits_cuda, and also returns how many bytes were outside {A,C,G,T,U,a,c,g,t,u} (the reference
+    maps those silently).  Returns (words, invalid_count)."""
+    src = _as_u8(n)
+    out = np.empty(words_for_len(src.size), dtype=np.uint64)
+    invalid = ctypes.c_uint64(0)
+    check(_lib.load().cn_n_to_bits_checked_host(src.ctypes.data, src.size, out.ctypes.data, ctypes.byref(invalid)))
+    return out, int(invalid.value)
 
 
 def bits_to_n_cuda(bits, length: int) -> bytes:
@@ -79,6 +89,22 @@ def encode_device(n, out=None, stream=None):
         raise ValueError("out must be a contiguous 8-byte-element tensor with ceil(len/32) elements")
     with torch.cuda.device(n.device):
         check(_lib.load().cn_encode_device(n.data_ptr(), length, out.data_ptr(), _stream_ptr(stream)))
+    return out
+
+
+def encode_checked_device(n, counter, out=None, stream=None):
+    """encode_device + validation: `counter` (one-element int64 CUDA tensor) is incremented by the number of
+    bytes outside the alphabet.  Asynchronous like encode_device; read the counter after synchronising."""
+    import torch
+    if n.dtype != torch.uint8 or not n.is_cuda or not n.is_contiguous():
+        raise TypeError("encode_checked_device expects a contiguous uint8 CUDA tensor")
+    if counter.element_size() != 8 or counter.numel() < 1 or not counter.is_cuda:
+        raise TypeError("counter must be a one-element 8-byte CUDA tensor")
+    length = n.numel()
+    if out is None:
+        out = torch.empty(words_for_len(length), dtype=torch.int64, device=n.device)
+    with torch.cuda.device(n.device):
+        check(_lib.load().cn_encode_checked_device(n.data_ptr(), length, out.data_ptr(), counter.data_ptr(), _stream_ptr(stream)))
     return out
 
 

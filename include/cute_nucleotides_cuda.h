@@ -78,6 +78,14 @@ CN_API int cn_encode_device(const void *d_n, size_t len, void *d_out, void *stre
 /* d_bits 8-byte aligned; d_out any alignment (16-byte aligned takes the fast path). */
 CN_API int cn_decode_device(const void *d_bits, size_t nwords, size_t len, void *d_out, void *stream);
 
+/* ---- encode + validation in one pass ---------------------------------------------------------- */
+/* The reference maps bytes outside {A,C,G,T,U,a,c,g,t,u} silently (LUT -> 0, SIMD -> (b>>1)&3; its README points to an
+ * external validity checker).  These entry points produce exactly the same packed words as cn_n_to_bits_host /
+ * cn_encode_device and additionally count the offending bytes, at no extra HBM traffic.
+ * Device flavour: *d_invalid_count (8-byte aligned uint64 in device memory) is INCREMENTED; zero it first. */
+CN_API int cn_n_to_bits_checked_host(const uint8_t *n, size_t len, uint64_t *out, uint64_t *invalid_count);
+CN_API int cn_encode_checked_device(const void *d_n, size_t len, void *d_out, void *d_invalid_count, void *stream);
+
 /* ---- base-5 codec: {A,C,T/U,G,N} -> digits 0..4, 3 digits -> 7 bits, 27 nucleotides per u64 ------------ */
 /* (len / 27) + (len % 27 != 0): words produced by n_to_bits2_* (src/n_to_bits2.rs:38, :121). */
 CN_API size_t cn_words2_for_len(size_t len);

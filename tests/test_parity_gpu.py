@@ -309,3 +309,95 @@ def test_config3_config4_ten_gib_properties(cn, oracle, torch_cuda):
     # idempotence: encode(decode(w)) == w for whole words
     re = cn.encode_device(d_dec[: 32 * (nwords - 1)])
     assert torch.equal(re, d_w[: nwords - 1])
+
+
+def test_host_api_is_thread_safe(cn, oracle):
+    """The reference functions are pure and callable from any thread (SURVEY 8b "Threading"); the C ABI keeps
+    per-thread staging.  Eight threads encode/decode different inputs concurrently (ctypes drops the GIL),
+    including threads that exit and are replaced (their staging must be released, not corrupted)."""
+    import threading
+    errors = []
+
+    def worker(seed):
+        try:
+            for rep in range(3):
+                size = 100003 + 4099 * seed + (1 << 20) * (rep == 2)
+                n = oracle.generate(size, seed=seed * 10 + rep, alphabet=10)
+                ref = oracle.n_to_bits(n, "lut")
+                got = cn.n_to_bits_cuda(n)
+                if not np.array_equal(got, ref) or cn.bits_to_n_cuda(got, size) != oracle.canonical(n):
+                    errors.append((seed, rep))
+                m = oracle.generate2(size // 3, seed=seed, alphabet=12)
+                if cn.bits_to_n2_cuda(cn.n_to_bits2_cuda(m), m.size) != oracle.canonical2(m):
+                    errors.append((seed, rep, "base5"))
+        except Exception as e:                      # noqa: BLE001
+            errors.append((seed, repr(e)))
+
+    for wave in range(2):
+        threads = [threading.Thread(target=worker, args=(wave * 8 + i,)) for i in range(8)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    assert not errors, errors
+
+
+# ---------------------------------------------------------------------------------------------------
+# encode + validation in one pass (SURVEY 8f-3)
+# ---------------------------------------------------------------------------------------------------
+def _with_garbage(oracle, size, seed, n_bad):
+    rng = np.random.default_rng(seed)
+    n = oracle.generate(size, seed=seed, alphabet=10).copy()
+    if size and n_bad:
+        pos = rng.choice(size, size=min(n_bad, size), replace=False)
+        junk = np.frombuffer(b"NnXx-.*0 \n@[`{BbDdHhVvSsWw\x00\x7f\x80\xff\xc3", dtype=np.uint8)
+        n[pos] = junk[rng.integers(0, junk.size, size=pos.size)]
+    return n
+
+
+@pytest.mark.parametrize("size,n_bad", [(0, 0), (1, 1), (31, 3), (32, 0), (33, 33), (1000, 17), (40000, 0), (40000, 1),
+                                        ((1 << 20) + 17, 5000), (3 * (1 << 20) + 5, 1)])
+def test_checked_encode_host(cn, oracle, size, n_bad):
+    n = _with_garbage(oracle, size, size + n_bad, n_bad)
+    words, invalid = cn.n_to_bits_checked_cuda(n)
+    assert invalid == oracle.count_invalid(n)
+    assert np.array_equal(words, cn.n_to_bits_cuda(n))                 # same packed words as the unchecked call
+    if invalid == 0:
+        assert np.array_equal(words, oracle.n_to_bits(n, "lut"))
+
+
+def test_checked_encode_every_byte_value(cn, oracle):
+    """All 256 byte values, each in its own 32-byte word among valid neighbours: exactly 246 are invalid."""
+    n = np.full(256 * 32, ord("A"), dtype=np.uint8)
+    n[np.arange(256) * 32 + (np.arange(256) % 32)] = np.arange(256, dtype=np.uint8)
+    words, invalid = cn.n_to_bits_checked_cuda(n)
+    assert invalid == 246 == oracle.count_invalid(n)
+    for b in range(256):
+        alone = np.full(64, ord("c"), dtype=np.uint8)
+        alone[b % 64] = b
+        assert cn.n_to_bits_checked_cuda(alone)[1] == (0 if bytes([b]) in [bytes([c]) for c in b"ACGTUacgtu"] else 1), b
+
+
+@pytest.mark.parametrize("in_off", [0, 3, 16, 21])
+def test_checked_encode_device(cn, oracle, torch_cuda, in_off):
+    torch = torch_cuda
+    from cute_nucleotides_b200 import _lib
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    for size, n_bad in ((5, 2), (4096 + 7, 9), ((1 << 22) + 3, 12345), ((1 << 22), 0)):
+        n = _with_garbage(oracle, size + 32, size, n_bad)
+        sl = n[in_off: in_off + size]
+        d_all = torch.from_numpy(n).cuda()
+        d_bits = torch.empty(cn.words_for_len(size), dtype=torch.int64, device="cuda")
+        counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+        _lib.check(lib.cn_encode_checked_device(d_all.data_ptr() + in_off, size, d_bits.data_ptr(), counter.data_ptr(), st))
+        assert int(counter.item()) == oracle.count_invalid(sl)
+        plain = torch.empty_like(d_bits)
+        _lib.check(lib.cn_encode_device(d_all.data_ptr() + in_off, size, plain.data_ptr(), st))
+        assert torch.equal(d_bits, plain)
+    # the tensor-level wrapper accumulates across calls
+    counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+    n = _with_garbage(oracle, 100000, 5, 77)
+    cn.encode_checked_device(torch.from_numpy(n).cuda(), counter)
+    cn.encode_checked_device(torch.from_numpy(n).cuda(), counter)
+    assert int(counter.item()) == 2 * oracle.count_invalid(n)
