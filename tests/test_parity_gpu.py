@@ -401,3 +401,70 @@ def test_checked_encode_device(cn, oracle, torch_cuda, in_off):
     cn.encode_checked_device(torch.from_numpy(n).cuda(), counter)
     cn.encode_checked_device(torch.from_numpy(n).cuda(), counter)
     assert int(counter.item()) == 2 * oracle.count_invalid(n)
+
+
+# ---------------------------------------------------------------------------------------------------
+# error behaviour of the C ABI: status codes + messages, never an abort
+# ---------------------------------------------------------------------------------------------------
+def test_abi_error_paths(cn, torch_cuda):
+    torch = torch_cuda
+    import ctypes
+    from cute_nucleotides_b200 import _lib
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    d = torch.zeros(256, dtype=torch.uint8, device="cuda")
+    w = torch.zeros(32, dtype=torch.int64, device="cuda")
+    # misaligned packed side
+    assert lib.cn_encode_device(d.data_ptr(), 64, w.data_ptr() + 4, st) == _lib.CN_ERR_ARG
+    assert b"8-byte aligned" in lib.cn_last_error()
+    assert lib.cn_decode_device(w.data_ptr() + 4, 2, 64, d.data_ptr(), st) == _lib.CN_ERR_ARG
+    assert lib.cn_encode2_device(d.data_ptr(), 54, w.data_ptr() + 4, st) == _lib.CN_ERR_ARG
+    # null pointers with non-zero length
+    assert lib.cn_encode_device(None, 64, w.data_ptr(), st) == _lib.CN_ERR_ARG
+    assert lib.cn_n_to_bits_host(None, 64, w.data_ptr()) == _lib.CN_ERR_ARG
+    assert lib.cn_bits_to_n_host(None, 2, 64, d.data_ptr()) == _lib.CN_ERR_ARG
+    assert lib.cn_encode_checked_device(d.data_ptr(), 64, w.data_ptr(), None, st) == _lib.CN_ERR_ARG
+    # the panic condition is a status code with the reference's text, for both codecs, host and device
+    assert lib.cn_decode_device(w.data_ptr(), 2, 65, d.data_ptr(), st) == _lib.CN_ERR_LENGTH
+    assert lib.cn_last_error() == lib.cn_length_panic_message()
+    assert lib.cn_decode2_device(w.data_ptr(), 2, 55, d.data_ptr(), st) == _lib.CN_ERR_LENGTH
+    assert lib.cn_bits_to_n2_host(w.data_ptr(), 2, 55, d.data_ptr()) == _lib.CN_ERR_LENGTH
+    # bad enums / devices
+    assert lib.cn_init(99) == _lib.CN_ERR_ARG and b"out of range" in lib.cn_last_error()
+    assert lib.cn_generate_device(d.data_ptr(), 0, 16, 1, 7, st) == _lib.CN_ERR_ARG
+    assert lib.cn_generate_device(d.data_ptr(), 3, 16, 1, 4, st) == _lib.CN_ERR_ARG
+    assert lib.cn_set_host_strategy(2, 0) == _lib.CN_ERR_ARG and lib.cn_set_host_strategy(0, 1000) == _lib.CN_ERR_ARG
+    count = ctypes.c_int()
+    assert lib.cn_device_count(ctypes.byref(count)) == 0 and count.value >= 1
+    # after all those failures the library still works
+    assert cn.n_to_bits_cuda(b"ATCG").tolist() == [0xD8]
+    torch.cuda.synchronize()
+
+
+def test_harness_allocators(cn):
+    """cn_device_malloc / cn_host_malloc_pinned / cn_memcpy_* / cn_time_*: the helpers the C++ / Rust harnesses use."""
+    import ctypes
+    from cute_nucleotides_b200 import _lib
+    lib = _lib.load()
+    n = (b"ATCGatcgUu" * 1000)[:9999]
+    d_n, d_w, h_w = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    words = cn.words_for_len(len(n))
+    _lib.check(lib.cn_device_malloc(ctypes.byref(d_n), len(n)))
+    _lib.check(lib.cn_device_malloc(ctypes.byref(d_w), words * 8))
+    _lib.check(lib.cn_host_malloc_pinned(ctypes.byref(h_w), words * 8))
+    _lib.check(lib.cn_memcpy_h2d(d_n, n, len(n), None))
+    ms = ctypes.c_float()
+    _lib.check(lib.cn_time_encode_device(d_n, len(n), d_w, 3, ctypes.byref(ms)))
+    assert ms.value > 0
+    _lib.check(lib.cn_memcpy_d2h(h_w, d_w, words * 8, None))
+    _lib.check(lib.cn_stream_synchronize(None))
+    got = np.ctypeslib.as_array(ctypes.cast(h_w, ctypes.POINTER(ctypes.c_uint64)), shape=(words,)).copy()
+    assert np.array_equal(got, cn.n_to_bits_cuda(n))
+    _lib.check(lib.cn_time_decode_device(d_w, words, len(n), d_n, 2, ctypes.byref(ms)))
+    back = ctypes.create_string_buffer(len(n))
+    _lib.check(lib.cn_memcpy_d2h(back, d_n, len(n), None))
+    _lib.check(lib.cn_stream_synchronize(None))
+    assert back.raw == n.upper().replace(b"U", b"T")
+    for p in (d_n, d_w):
+        _lib.check(lib.cn_device_free(p))
+    _lib.check(lib.cn_host_free_pinned(h_w))
