@@ -53,3 +53,41 @@ def test_sharded_encode_assemble_decode_nccl(tmp_path, total, granule):
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(world, _free_port(), total, granule, str(tmp_path)), nprocs=world, join=True)
     assert [open(tmp_path / f"rank{r}").read() for r in range(world)] == ["ok"] * world
+
+
+def test_one_process_two_gpus_via_cn_init(tmp_path):
+    """The host-slice calls run on the device the calling thread selected with cn_init(): two threads of ONE process
+    drive two GPUs (and two PCIe links) at once, each with its own thread-local staging."""
+    import threading
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+    import cute_nucleotides_b200 as cn
+    from cute_nucleotides_b200 import _lib
+    lib = _lib.load()
+    orc = _oracle.Oracle()
+    total = (1 << 24) + 77
+    whole = orc.generate(total, seed=3, alphabet=10)
+    from cute_nucleotides_b200 import sharded
+    out = np.zeros(cn.words_for_len(total), dtype=np.uint64)
+    errors = []
+
+    def worker(dev):
+        try:
+            _lib.check(lib.cn_init(dev))
+            s, e = sharded.shard_bounds(total, 2, dev, 1 << 20)
+            ws, we = sharded.word_bounds(total, 2, dev, 1 << 20)
+            out[ws:we] = cn.n_to_bits_cuda(whole[s:e])
+        except Exception as ex:      # noqa: BLE001
+            errors.append(repr(ex))
+
+    threads = [threading.Thread(target=worker, args=(d,)) for d in (0, 1)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert np.array_equal(out, orc.encode_mt(whole, "lut"))
