@@ -1,0 +1,297 @@
+// cn_launch.cuh -- device-resident entry points: pick a kernel instantiation for the pointers' alignment and the
+// current tuning, launch it on the caller's stream.  One launch per call, no synchronisation, no allocation.
+#pragma once
+#include "cn_common.cuh"
+#include "codec_kernels.cuh"
+#include "codec5_kernels.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// tuning state (process-wide, set once by harnesses; plain loads on the hot path)
+// ------------------------------------------------------------------------------------------------
+struct Tuning { int vec, unroll, threads; };
+// measured best on B200 (profiles/tune_r01.jsonl): 256-bit accesses, one vector per thread, 256 threads
+Tuning g_tune[2] = {{32, 1, 256}, {32, 1, 256}};
+int g_host_strategy = 0;
+size_t g_host_chunk = (size_t)16 << 20;      // ASCII bytes per pipeline chunk
+size_t g_host_small = (size_t)256 << 10;     // nucleotides at or below which the single-launch path is used
+
+bool tuning_ok(int vec, int unroll, int threads)
+{
+    return (vec == 16 || vec == 32) && (unroll == 1 || unroll == 2 || unroll == 4 || unroll == 8) &&
+           (threads == 128 || threads == 256 || threads == 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch plumbing
+// ------------------------------------------------------------------------------------------------
+struct EncArgs {
+    const uint8_t *in; uint32_t *out32; size_t nvec;
+    const uint8_t *n0; size_t len, edge_first, edge_total; unsigned shift_bytes;
+};
+struct DecArgs {
+    const uint32_t *bits32; uint8_t *out; size_t nvec; unsigned code_shift;
+    uint8_t *out0; size_t head, edge_from, len;
+};
+
+constexpr size_t kMaxGrid = 0x7FFFFFFFull;
+
+template <int VEC, int U, int T, bool MIS>
+cudaError_t enc_launch(const EncArgs &a, cudaStream_t s)
+{
+    size_t tile = (size_t)U * T;
+    size_t blocks = (a.nvec + tile - 1) / tile;
+    if (blocks == 0) blocks = 1;                       // the ragged end still needs its warp
+    if (blocks > kMaxGrid) return cudaErrorInvalidConfiguration;
+    cn::encode_kernel<VEC, U, T, MIS><<<(unsigned)blocks, T, 0, s>>>(a.in, a.out32, a.nvec, a.n0, a.len,
+                                                                    a.edge_first, a.edge_total, a.shift_bytes, nullptr);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+template <int VEC, int U, int T, bool MIS>
+cudaError_t dec_launch(const DecArgs &a, cudaStream_t s)
+{
+    size_t tile = (size_t)U * T;
+    size_t blocks = (a.nvec + tile - 1) / tile;
+    if (blocks == 0) blocks = 1;
+    if (blocks > kMaxGrid) return cudaErrorInvalidConfiguration;
+    cn::decode_kernel<VEC, U, T, MIS><<<(unsigned)blocks, T, 0, s>>>(a.bits32, a.out, a.nvec, a.code_shift, a.out0,
+                                                                    a.head, a.edge_from, a.len);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+template <bool ENC, int VEC, int U, typename A>
+cudaError_t pick_threads(int threads, const A &a, cudaStream_t s)
+{
+    if constexpr (ENC) {
+        switch (threads) {
+        case 128: return enc_launch<VEC, U, 128, false>(a, s);
+        case 512: return enc_launch<VEC, U, 512, false>(a, s);
+        default:  return enc_launch<VEC, U, 256, false>(a, s);
+        }
+    } else {
+        switch (threads) {
+        case 128: return dec_launch<VEC, U, 128, false>(a, s);
+        case 512: return dec_launch<VEC, U, 512, false>(a, s);
+        default:  return dec_launch<VEC, U, 256, false>(a, s);
+        }
+    }
+}
+template <bool ENC, int VEC, typename A>
+cudaError_t pick_unroll(const Tuning &t, const A &a, cudaStream_t s)
+{
+    switch (t.unroll) {
+    case 1:  return pick_threads<ENC, VEC, 1>(t.threads, a, s);
+    case 2:  return pick_threads<ENC, VEC, 2>(t.threads, a, s);
+    case 8:  return pick_threads<ENC, VEC, 8>(t.threads, a, s);
+    default: return pick_threads<ENC, VEC, 4>(t.threads, a, s);
+    }
+}
+
+// The tuning asked for 256-bit accesses but the pointer is only 16-byte aligned: use 128-bit accesses
+// and twice the unroll so each thread keeps the same number of bytes in flight.
+inline Tuning narrow(Tuning t)
+{
+    if (t.vec == 32) { t.vec = 16; if (t.unroll < 8) t.unroll *= 2; }
+    return t;
+}
+
+int encode_device(const void *d_n, size_t len, void *d_out, cudaStream_t s)
+{
+    if (len == 0) return CN_OK;
+    if (!d_n || !d_out) return fail(CN_ERR_ARG, "cn_encode_device: null pointer");
+    if (addr(d_out) & 7) return fail(CN_ERR_ARG, "cn_encode_device: output must be 8-byte aligned");
+    const Tuning t = g_tune[CN_DIR_ENCODE];
+    const size_t total32 = cn_words_for_len(len) * 2;          // output u32 units
+    EncArgs a{};
+    a.n0 = static_cast<const uint8_t *>(d_n);
+    a.len = len;
+    a.out32 = static_cast<uint32_t *>(d_out);
+    a.edge_total = total32;
+    cudaError_t e;
+    const unsigned mis = (unsigned)(addr(d_n) & 15);
+    if (mis == 0) {
+        a.in = a.n0;
+        if (t.vec == 32 && (addr(d_n) & 31) == 0) {
+            a.nvec = len >> 5;
+            a.edge_first = a.nvec * 2;
+            e = pick_unroll<true, 32>(t, a, s);
+        } else {
+            a.nvec = len >> 4;
+            a.edge_first = a.nvec;
+            e = pick_unroll<true, 16>(narrow(t), a, s);
+        }
+    } else {
+        // the body reads aligned vectors i and i+1 for group i; keep both inside [d_n, d_n + len)
+        size_t spans = (len + mis) >> 4;
+        a.in = a.n0 - mis;
+        a.shift_bytes = mis;
+        a.nvec = spans > 0 ? spans - 1 : 0;
+        a.edge_first = a.nvec;
+        e = enc_launch<16, 4, 256, true>(a, s);
+    }
+    if (e != cudaSuccess) return fail(CN_ERR_CUDA, "encode kernel launch failed: %s", cudaGetErrorString(e));
+    return CN_OK;
+}
+
+// encode + validation in one pass (fixed launch shapes: the measured-best ones)
+template <int VEC, int U, int T, bool MIS>
+cudaError_t enc_launch_checked(const EncArgs &a, unsigned long long *counter, cudaStream_t s)
+{
+    size_t tile = (size_t)U * T;
+    size_t blocks = (a.nvec + tile - 1) / tile;
+    if (blocks == 0) blocks = 1;
+    if (blocks > kMaxGrid) return cudaErrorInvalidConfiguration;
+    cn::encode_kernel<VEC, U, T, MIS, true><<<(unsigned)blocks, T, 0, s>>>(a.in, a.out32, a.nvec, a.n0, a.len,
+                                                                          a.edge_first, a.edge_total, a.shift_bytes, counter);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+int encode_checked_device(const void *d_n, size_t len, void *d_out, void *d_invalid, cudaStream_t s)
+{
+    if (!d_invalid || (addr(d_invalid) & 7)) return fail(CN_ERR_ARG, "cn_encode_checked_device: counter must be a non-null 8-byte aligned device pointer");
+    if (len == 0) return CN_OK;
+    if (!d_n || !d_out) return fail(CN_ERR_ARG, "cn_encode_checked_device: null pointer");
+    if (addr(d_out) & 7) return fail(CN_ERR_ARG, "cn_encode_checked_device: output must be 8-byte aligned");
+    unsigned long long *counter = static_cast<unsigned long long *>(d_invalid);
+    EncArgs a{};
+    a.n0 = static_cast<const uint8_t *>(d_n);
+    a.len = len;
+    a.out32 = static_cast<uint32_t *>(d_out);
+    a.edge_total = cn_words_for_len(len) * 2;
+    cudaError_t e;
+    const unsigned mis = (unsigned)(addr(d_n) & 15);
+    if (mis == 0) {
+        a.in = a.n0;
+        if ((addr(d_n) & 31) == 0) {
+            a.nvec = len >> 5;
+            a.edge_first = a.nvec * 2;
+            e = enc_launch_checked<32, 1, 256, false>(a, counter, s);
+        } else {
+            a.nvec = len >> 4;
+            a.edge_first = a.nvec;
+            e = enc_launch_checked<16, 2, 256, false>(a, counter, s);
+        }
+    } else {
+        size_t spans = (len + mis) >> 4;
+        a.in = a.n0 - mis;
+        a.shift_bytes = mis;
+        a.nvec = spans > 0 ? spans - 1 : 0;
+        a.edge_first = a.nvec;
+        e = enc_launch_checked<16, 4, 256, true>(a, counter, s);
+    }
+    if (e != cudaSuccess) return fail(CN_ERR_CUDA, "checked encode kernel launch failed: %s", cudaGetErrorString(e));
+    return CN_OK;
+}
+
+int decode_device(const void *d_bits, size_t nwords, size_t len, void *d_out, cudaStream_t s)
+{
+    if (len > (nwords << 5) || (nwords >> 59) != 0) return fail(CN_ERR_LENGTH, "%s", kPanicText);
+    if (len == 0) return CN_OK;
+    if (!d_bits || !d_out) return fail(CN_ERR_ARG, "cn_decode_device: null pointer");
+    if (addr(d_bits) & 7) return fail(CN_ERR_ARG, "cn_decode_device: packed input must be 8-byte aligned");
+    const Tuning t = g_tune[CN_DIR_DECODE];
+    DecArgs a{};
+    a.bits32 = static_cast<const uint32_t *>(d_bits);
+    a.out0 = static_cast<uint8_t *>(d_out);
+    a.len = len;
+    cudaError_t e;
+    const unsigned mis = (unsigned)(addr(d_out) & 15);
+    if (mis == 0) {
+        a.out = a.out0;
+        if (t.vec == 32 && (addr(d_out) & 31) == 0) {
+            a.nvec = len >> 5;
+            a.edge_from = a.nvec << 5;
+            e = pick_unroll<false, 32>(t, a, s);
+        } else {
+            a.nvec = len >> 4;
+            a.edge_from = a.nvec << 4;
+            e = pick_unroll<false, 16>(narrow(t), a, s);
+        }
+    } else {
+        size_t head = 16 - mis;                    // nucleotides until the destination is 16-byte aligned
+        if (head > len) head = len;
+        a.head = head;
+        a.out = a.out0 + head;
+        a.code_shift = (unsigned)(2 * head);
+        a.nvec = (len - head) >> 4;
+        a.edge_from = head + (a.nvec << 4);
+        e = dec_launch<16, 4, 256, true>(a, s);
+    }
+    if (e != cudaSuccess) return fail(CN_ERR_CUDA, "decode kernel launch failed: %s", cudaGetErrorString(e));
+    return CN_OK;
+}
+
+// ---- base-5 codec (src/n_to_bits2.rs) ----------------------------------------------------------------
+// Tile staging of the base-5 kernels: bit 0 = cp.async.bulk (TMA) tile load in encode, bit 1 = TMA tile store in
+// decode.  Measured on B200 at 10 GiB (profiles/codec5_r01.json): LDG/STS staging 6118 / 6500 GB/s, TMA 6870 / 6712 GB/s,
+// so TMA is the default; CN_B5_TMA=0..3 selects the alternatives for A/B runs.
+const int g_b5_tma = std::getenv("CN_B5_TMA") ? std::atoi(std::getenv("CN_B5_TMA")) : 3;
+
+inline size_t words2_for_len(size_t len) { return len / 27 + ((len % 27) ? 1 : 0); }
+
+int encode2_device(const void *d_n, size_t len, void *d_out, cudaStream_t s)
+{
+    if (len == 0) return CN_OK;
+    if (!d_n || !d_out) return fail(CN_ERR_ARG, "cn_encode2_device: null pointer");
+    if (addr(d_out) & 7) return fail(CN_ERR_ARG, "cn_encode2_device: output must be 8-byte aligned");
+    const size_t total = words2_for_len(len);
+    const uint8_t *in = static_cast<const uint8_t *>(d_n);
+    uint64_t *out = static_cast<uint64_t *>(d_out);
+    if ((addr(d_n) & 15) == 0 && (addr(d_out) & 31) == 0) {                  // 128-bit ASCII loads, 256-bit packed stores
+        const size_t ntiles = (len / 27) / cn::kB5WarpWords;                 // tiles of complete words
+        const size_t blocks = (ntiles + 1 + cn::kB5Warps - 1) / cn::kB5Warps;
+        if (blocks > kMaxGrid) return fail(CN_ERR_ARG, "cn_encode2_device: input too large for one launch");
+        if (g_b5_tma & 1) cn::b5_encode_kernel<true><<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(in, out, len, ntiles, total);
+        else cn::b5_encode_kernel<false><<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(in, out, len, ntiles, total);
+    } else {
+        size_t blocks = (total + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        cn::b5_encode_scalar_kernel<<<(unsigned)blocks, 256, 0, s>>>(in, out, len, total);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(CN_ERR_CUDA, "base-5 encode kernel launch failed: %s", cudaGetErrorString(e));
+    return CN_OK;
+}
+
+int decode2_device(const void *d_bits, size_t nwords, size_t len, void *d_out, cudaStream_t s)
+{
+    if (nwords > (~(size_t)0) / 27 || len > nwords * 27) return fail(CN_ERR_LENGTH, "%s", kPanicText);   // n_to_bits2.rs:79-81
+    if (len == 0) return CN_OK;
+    if (!d_bits || !d_out) return fail(CN_ERR_ARG, "cn_decode2_device: null pointer");
+    if (addr(d_bits) & 7) return fail(CN_ERR_ARG, "cn_decode2_device: packed input must be 8-byte aligned");
+    const size_t total = words2_for_len(len);
+    const uint64_t *bits = static_cast<const uint64_t *>(d_bits);
+    uint8_t *out = static_cast<uint8_t *>(d_out);
+    if ((addr(d_out) & 15) == 0 && (addr(d_bits) & 31) == 0) {
+        const size_t ntiles = (len / 27) / cn::kB5WarpWords;
+        const size_t blocks = (ntiles + 1 + cn::kB5Warps - 1) / cn::kB5Warps;
+        if (blocks > kMaxGrid) return fail(CN_ERR_ARG, "cn_decode2_device: input too large for one launch");
+        if (g_b5_tma & 2) cn::b5_decode_kernel<true><<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(bits, out, len, ntiles, total);
+        else cn::b5_decode_kernel<false><<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(bits, out, len, ntiles, total);
+    } else {
+        size_t blocks = (total + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        cn::b5_decode_scalar_kernel<<<(unsigned)blocks, 256, 0, s>>>(bits, out, len, total);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(CN_ERR_CUDA, "base-5 decode kernel launch failed: %s", cudaGetErrorString(e));
+    return CN_OK;
+}
+
+// What the host pipeline needs to know about a codec: nucleotides per word and the device entry points.
+struct Codec {
+    unsigned group;                                                        // 32 (2-bit) or 27 (base-5)
+    int (*enc)(const void *, size_t, void *, cudaStream_t);
+    int (*dec)(const void *, size_t, size_t, void *, cudaStream_t);
+    size_t words(size_t nt) const { return nt / group + ((nt % group) ? 1 : 0); }
+};
+const Codec kCodec2bit{32, encode_device, decode_device};
+const Codec kCodecBase5{27, encode2_device, decode2_device};
+
+}  // namespace
