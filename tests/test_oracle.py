@@ -154,3 +154,27 @@ def test_config1_one_mib_roundtrip_on_cpu(oracle):
     words = oracle.n_to_bits(n, "lut")
     assert words.size == 32768
     assert oracle.bits_to_n(words, n.size, "lut") == n.tobytes()
+
+
+def test_property_roundtrip_and_shard_linearity(oracle):
+    """Property checks with hypothesis: decode(encode(x)) == canonical(x); encoding is linear over concatenation at
+    word boundaries (what makes sharding by offset exact); every restated variant agrees with the scalar pair."""
+    from hypothesis import given, settings, strategies as st
+    alphabet = st.sampled_from(list(b"ACGTUacgtu"))
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(alphabet, max_size=300), st.integers(min_value=0, max_value=9))
+    def check(chars, cut_words):
+        n = bytes(chars)
+        words = oracle.n_to_bits(n, "lut")
+        assert oracle.bits_to_n(words, len(n), "lut") == oracle.canonical(n)
+        cut = min(len(n), 32 * cut_words)
+        left, right = oracle.n_to_bits(n[:cut], "lut"), oracle.n_to_bits(n[cut:], "lut")
+        assert np.array_equal(np.concatenate([left, right]), words)
+        if oracle.simd_ok:
+            for v in ("pext", "shift", "movemask", "mul"):
+                assert np.array_equal(oracle.n_to_bits(n, v), words)
+            for v in ("shuffle", "pdep", "clmul"):
+                assert oracle.bits_to_n(words, len(n), v) == oracle.canonical(n)
+
+    check()

@@ -468,3 +468,41 @@ def test_harness_allocators(cn):
     for p in (d_n, d_w):
         _lib.check(lib.cn_device_free(p))
     _lib.check(lib.cn_host_free_pinned(h_w))
+
+
+def test_fuzz_sizes_and_alignments(cn, oracle, torch_cuda):
+    """300 random (length, source offset, destination offset) triples through the device entry points of both
+    codecs, with guard bytes, bit-exact against the oracle.  Seeded: failures reproduce."""
+    torch = torch_cuda
+    from cute_nucleotides_b200 import _lib
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(20261017)
+    pool = oracle.generate(1 << 21, seed=123, alphabet=10)
+    pool5 = oracle.generate2(1 << 21, seed=321, alphabet=12)
+    d_pool = torch.from_numpy(pool).cuda()
+    d_pool5 = torch.from_numpy(pool5).cuda()
+    d_words = torch.empty((1 << 17) + 8, dtype=torch.int64, device="cuda")
+    d_out = torch.empty((1 << 21) + 128, dtype=torch.uint8, device="cuda")
+    for it in range(300):
+        scale = [64, 4096, 1 << 17, 1 << 20][it % 4]
+        size = int(rng.integers(0, scale))
+        src_off = int(rng.integers(0, 64))
+        dst_off = int(rng.integers(0, 64))
+        base5 = bool(it & 1)
+        host = (pool5 if base5 else pool)[src_off: src_off + size]
+        d_src = (d_pool5 if base5 else d_pool).data_ptr() + src_off
+        ref = oracle.n_to_bits2(host, "lut") if base5 else oracle.n_to_bits(host, "lut")
+        d_words.fill_(-1)
+        d_out.fill_(0x7E)
+        enc = lib.cn_encode2_device if base5 else lib.cn_encode_device
+        dec = lib.cn_decode2_device if base5 else lib.cn_decode_device
+        _lib.check(enc(d_src, size, d_words.data_ptr(), st))
+        got = d_words[: ref.size + 1].cpu().numpy().view(np.uint64)
+        assert np.array_equal(got[: ref.size], ref), (it, size, src_off, base5)
+        assert got[ref.size] == np.uint64(0xFFFFFFFFFFFFFFFF), (it, size, src_off, base5)
+        _lib.check(dec(d_words.data_ptr(), ref.size, size, d_out.data_ptr() + dst_off, st))
+        h = d_out[: dst_off + size + 64].cpu().numpy()
+        canon = oracle.canonical2(host) if base5 else oracle.canonical(host)
+        assert h[dst_off: dst_off + size].tobytes() == canon, (it, size, dst_off, base5)
+        assert np.all(h[:dst_off] == 0x7E) and np.all(h[dst_off + size:] == 0x7E), (it, size, dst_off, base5)
