@@ -29,6 +29,10 @@ PROTOTYPES = {
     "cn_bits_to_n_host": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p]),
     "cn_encode_device": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "cn_decode_device": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
+    "cn_encode_multi_device": (c_int, [c_void_p, c_size_t, POINTER(c_void_p), c_int, c_void_p]),
+    "cn_ipc_export": (c_int, [c_void_p, c_void_p, POINTER(c_size_t)]),
+    "cn_ipc_open": (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
+    "cn_ipc_close": (c_int, [c_void_p, c_size_t]),
     "cn_n_to_bits_checked_host": (c_int, [c_void_p, c_size_t, c_void_p, POINTER(c_uint64)]),
     "cn_encode_checked_device": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "cn_words2_for_len": (c_size_t, [c_size_t]),

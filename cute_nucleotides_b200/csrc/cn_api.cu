@@ -88,6 +88,14 @@ int cn_encode_checked_device(const void *d_n, size_t len, void *d_out, void *d_i
     return encode_checked_device(d_n, len, d_out, d_invalid_count, static_cast<cudaStream_t>(stream));
 }
 
+int cn_encode_multi_device(const void *d_n, size_t len, void *const *d_outs, int nout, void *stream)
+{
+    return encode_multi_device(d_n, len, d_outs, nout, static_cast<cudaStream_t>(stream));
+}
+int cn_ipc_export(void *d_ptr, void *handle64, size_t *offset) { return ipc_export(d_ptr, handle64, offset); }
+int cn_ipc_open(const void *handle64, size_t offset, void **d_ptr) { return ipc_open(handle64, offset, d_ptr); }
+int cn_ipc_close(void *d_ptr, size_t offset) { return ipc_close(d_ptr, offset); }
+
 int cn_encode_device(const void *d_n, size_t len, void *d_out, void *stream)
 {
     return encode_device(d_n, len, d_out, static_cast<cudaStream_t>(stream));

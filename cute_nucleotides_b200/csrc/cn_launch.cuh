@@ -187,6 +187,70 @@ int encode_checked_device(const void *d_n, size_t len, void *d_out, void *d_inva
     return CN_OK;
 }
 
+int encode_multi_device(const void *d_n, size_t len, void *const *d_outs, int nout, cudaStream_t s)
+{
+    if (nout < 1 || nout > cn::kMaxPeers || !d_outs) return fail(CN_ERR_ARG, "cn_encode_multi_device: 1..%d destinations", cn::kMaxPeers);
+    if (len == 0) return CN_OK;
+    if (!d_n || (addr(d_n) & 31)) return fail(CN_ERR_ARG, "cn_encode_multi_device: input must be 32-byte aligned");
+    cn::PeerOuts outs{};
+    for (int d = 0; d < nout; d++) {
+        if (!d_outs[d] || (addr(d_outs[d]) & 7)) return fail(CN_ERR_ARG, "cn_encode_multi_device: destination %d null or not 8-byte aligned", d);
+        outs.p[d] = static_cast<uint32_t *>(d_outs[d]);
+    }
+    const size_t nvec = len >> 5;
+    size_t blocks = (nvec + 255) / 256;
+    if (blocks == 0) blocks = 1;
+    if (blocks > kMaxGrid) return fail(CN_ERR_ARG, "cn_encode_multi_device: input too large for one launch");
+    cn::encode_multi_kernel<256><<<(unsigned)blocks, 256, 0, s>>>(static_cast<const uint8_t *>(d_n), outs, nout, nvec, len,
+                                                                 nvec * 2, cn_words_for_len(len) * 2);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(CN_ERR_CUDA, "multi-destination encode launch failed: %s", cudaGetErrorString(e));
+    return CN_OK;
+}
+
+// ---- CUDA IPC: let another process (one process per GPU) map a buffer of this one -----------------------
+// cudaIpcGetMemHandle describes the whole ALLOCATION that contains a pointer; a tensor handed out by a caching
+// allocator may sit at an offset inside it, so the offset is exported alongside (cuMemGetAddressRange, resolved at
+// run time so the library has no link-time dependency on libcuda).
+int ipc_export(void *d_ptr, void *handle64, size_t *offset)
+{
+    if (!d_ptr || !handle64 || !offset) return fail(CN_ERR_ARG, "cn_ipc_export: null pointer");
+    typedef int (*GetRange)(unsigned long long *, size_t *, unsigned long long);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CN_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q));
+    if (!fn) return fail(CN_ERR_CUDA, "cn_ipc_export: cuMemGetAddressRange unavailable");
+    unsigned long long base = 0;
+    size_t size = 0;
+    int rc = reinterpret_cast<GetRange>(fn)(&base, &size, (unsigned long long)addr(d_ptr));
+    if (rc != 0) return fail(CN_ERR_CUDA, "cn_ipc_export: cuMemGetAddressRange failed (%d)", rc);
+    cudaIpcMemHandle_t h;
+    CN_CUDA(cudaIpcGetMemHandle(&h, reinterpret_cast<void *>(base)));
+    static_assert(sizeof h == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, sizeof h);
+    *offset = (size_t)(addr(d_ptr) - base);
+    return CN_OK;
+}
+
+int ipc_open(const void *handle64, size_t offset, void **d_ptr)
+{
+    if (!handle64 || !d_ptr) return fail(CN_ERR_ARG, "cn_ipc_open: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof h);
+    void *base = nullptr;
+    CN_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    *d_ptr = static_cast<uint8_t *>(base) + offset;
+    return CN_OK;
+}
+
+int ipc_close(void *d_ptr, size_t offset)
+{
+    if (!d_ptr) return CN_OK;
+    CN_CUDA(cudaIpcCloseMemHandle(static_cast<uint8_t *>(d_ptr) - offset));
+    return CN_OK;
+}
+
 int decode_device(const void *d_bits, size_t nwords, size_t len, void *d_out, cudaStream_t s)
 {
     if (len > (nwords << 5) || (nwords >> 59) != 0) return fail(CN_ERR_LENGTH, "%s", kPanicText);

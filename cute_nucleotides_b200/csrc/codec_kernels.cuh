@@ -308,6 +308,34 @@ encode_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out32, size
 }
 
 // ------------------------------------------------------------------------------------------------
+// encode + assemble in one kernel (multi-GPU): the shard is read from local HBM ONCE and every packed u64 is
+// stored to up to kMaxPeers destinations -- the rank's own assembled buffer and the peer-mapped buffers of
+// the other ranks (CUDA IPC mappings; the stores travel over NVLink / NVSwitch).  Replaces "encode, then
+// all-gather": no intermediate packed shard, no separate collective, and the link transfer overlaps the HBM
+// reads.  `in` must be 32-byte aligned; each destination pointer is already offset to this shard's first word.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;
+struct PeerOuts { uint32_t *p[kMaxPeers]; };
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+encode_multi_kernel(const uint8_t *__restrict__ in, PeerOuts outs, int nout, size_t nvec,
+                    size_t len, size_t edge_first, size_t edge_total)
+{
+    const size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x;
+    if (i < nvec) {
+        u32x8 v = ld_stream32(in + (i << 5));
+        const uint32_t lo = pack16(v.v[0], v.v[1], v.v[2], v.v[3]), hi = pack16(v.v[4], v.v[5], v.v[6], v.v[7]);
+#pragma unroll
+        for (int d = 0; d < kMaxPeers; d++)
+            if (d < nout) st_stream8(outs.p[d] + (i << 1), lo, hi);
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x >= THREADS - 32) {
+        for (int d = 0; d < nout; d++) encode_edge(in, len, outs.p[d], edge_first, edge_total, threadIdx.x & 31);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // decode body.  VEC = ASCII bytes produced per thread per store (16 -> LDG.32 + STG.128,
 // 32 -> LDG.64 + STG.256).
 //   bits32     : packed stream as u32 (16 codes each)

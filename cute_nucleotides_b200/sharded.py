@@ -98,3 +98,69 @@ def decode_sharded(full_words, total_len: int, group=None, granule: int = GRANUL
     start, end = shard_bounds(total_len, world, rank, granule)
     ws, we = word_bounds(total_len, world, rank, granule)
     return n_to_bits.decode_device(full_words[ws:we], end - start)
+
+
+class PeerAssembly:
+    """Encode + assemble in ONE kernel per rank over NVLink peer memory (SURVEY 8e "fused option").
+
+    Every rank owns a full-size packed buffer; the buffers are mapped into every other rank's address space with
+    CUDA IPC (handles exchanged through torch.distributed), and `encode(n_shard)` launches a single kernel that reads
+    the local shard once and stores each packed word into ALL ranks' buffers at the shard's word offset -- no
+    intermediate packed shard, no NCCL collective on the data path.  `finish()` is the only synchronisation: it
+    waits for the local kernel and then for every rank's (a barrier), after which `self.full` holds the whole
+    packed sequence on every rank.  Needs one process per GPU on one NVLink-connected box (world <= 8)."""
+
+    def __init__(self, total_len: int, group=None, granule: int = 1 << 20):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+
+        self._lib, self._ctypes, self._torch, self._dist = _lib, ctypes, torch, dist
+        self.lib = _lib.load()
+        self.group, self.total_len, self.granule = group, total_len, granule
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("PeerAssembly supports at most 8 ranks (one NVSwitch domain)")
+        self.full = torch.empty(words_for_len(total_len), dtype=torch.int64, device="cuda")
+        handle = ctypes.create_string_buffer(64)
+        offset = ctypes.c_size_t()
+        _lib.check(self.lib.cn_ipc_export(self.full.data_ptr(), handle, ctypes.byref(offset)))
+        mine = (bytes(handle.raw), int(offset.value))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        self._opened = []
+        self.peer_ptrs = []
+        for r, (h, off) in enumerate(everyone):
+            if r == self.rank:
+                self.peer_ptrs.append(self.full.data_ptr())
+                continue
+            p = ctypes.c_void_p()
+            _lib.check(self.lib.cn_ipc_open(h, off, ctypes.byref(p)))
+            self._opened.append((p.value, off))
+            self.peer_ptrs.append(p.value)
+        dist.barrier(group=group)
+
+    def encode(self, n_shard, stream=None):
+        """Launch the fused kernel for this rank's shard (asynchronous)."""
+        torch, ctypes = self._torch, self._ctypes
+        start, end = shard_bounds(self.total_len, self.world, self.rank, self.granule)
+        if n_shard.numel() != end - start or n_shard.dtype != torch.uint8 or not n_shard.is_cuda:
+            raise ValueError(f"rank {self.rank}: shard must be the uint8 CUDA tensor of nucleotides [{start}, {end})")
+        word_off = (start >> 5) * 8
+        outs = (ctypes.c_void_p * self.world)(*[p + word_off for p in self.peer_ptrs])
+        s = stream if stream is not None else torch.cuda.current_stream()
+        self._lib.check(self.lib.cn_encode_multi_device(n_shard.data_ptr(), end - start, outs, self.world, s.cuda_stream))
+
+    def finish(self):
+        """Wait until every rank's stores have landed everywhere; returns the assembled tensor."""
+        self._torch.cuda.synchronize()
+        self._dist.barrier(group=self.group)
+        return self.full
+
+    def close(self):
+        self._torch.cuda.synchronize()
+        self._dist.barrier(group=self.group)
+        for p, off in self._opened:
+            self.lib.cn_ipc_close(p, off)
+        self._opened = []

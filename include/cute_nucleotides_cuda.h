@@ -78,6 +78,17 @@ CN_API int cn_encode_device(const void *d_n, size_t len, void *d_out, void *stre
 /* d_bits 8-byte aligned; d_out any alignment (16-byte aligned takes the fast path). */
 CN_API int cn_decode_device(const void *d_bits, size_t nwords, size_t len, void *d_out, void *stream);
 
+/* ---- multi-GPU: encode + assemble in ONE kernel over NVLink peer memory (one process per GPU) ---------------- */
+/* Reads the shard once and stores every packed word to `nout` (1..8) destinations: the caller's own assembled buffer
+ * and peer buffers mapped with cn_ipc_open.  Each d_outs[k] is a device pointer ALREADY offset to this shard's first
+ * word.  d_n must be 32-byte aligned.  Replaces cn_encode_device + an all-gather of the packed shards. */
+CN_API int cn_encode_multi_device(const void *d_n, size_t len, void *const *d_outs, int nout, void *stream);
+/* CUDA IPC plumbing for the above: export a device pointer as a 64-byte handle + offset inside its allocation
+ * (send them to the peer process), map it there, unmap it. */
+CN_API int cn_ipc_export(void *d_ptr, void *handle64, size_t *offset);
+CN_API int cn_ipc_open(const void *handle64, size_t offset, void **d_ptr);
+CN_API int cn_ipc_close(void *d_ptr, size_t offset);
+
 /* ---- encode + validation in one pass ---------------------------------------------------------- */
 /* The reference maps bytes outside {A,C,G,T,U,a,c,g,t,u} silently (LUT -> 0, SIMD -> (b>>1)&3; its README points to an
  * external validity checker).  These entry points produce exactly the same packed words as cn_n_to_bits_host /
