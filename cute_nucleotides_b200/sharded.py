@@ -152,6 +152,18 @@ class PeerAssembly:
         s = stream if stream is not None else torch.cuda.current_stream()
         self._lib.check(self.lib.cn_encode_multi_device(n_shard.data_ptr(), end - start, outs, self.world, s.cuda_stream))
 
+    def decode_from(self, source_rank: int, stream=None):
+        """Scatter/broadcast + decode in one kernel: decode THIS rank's range of the packed sequence reading the words
+        straight out of `source_rank`'s buffer (peer loads over NVLink) -- no copy of the packed words first."""
+        torch = self._torch
+        start, end = shard_bounds(self.total_len, self.world, self.rank, self.granule)
+        ws, we = word_bounds(self.total_len, self.world, self.rank, self.granule)
+        out = torch.empty(end - start, dtype=torch.uint8, device="cuda")
+        s = stream if stream is not None else torch.cuda.current_stream()
+        self._lib.check(self.lib.cn_decode_device(self.peer_ptrs[source_rank] + ws * 8, we - ws, end - start,
+                                                  out.data_ptr(), s.cuda_stream))
+        return out
+
     def finish(self):
         """Wait until every rank's stores have landed everywhere; returns the assembled tensor."""
         self._torch.cuda.synchronize()

@@ -119,6 +119,10 @@ def _fused_worker(rank, world, port, total, granule, result_dir):
         ok = np.array_equal(full.cpu().numpy().view(np.uint64), orc.encode_mt(whole, "lut"))
         nccl = sharded.encode_sharded(d_shard, total, assemble=True, granule=granule)
         ok = ok and bool(torch.equal(nccl, full))
+        # decode this rank's range straight out of ANOTHER rank's buffer (peer loads over NVLink)
+        remote = asm.decode_from((rank + 1) % world)
+        torch.cuda.synchronize()
+        ok = ok and remote.cpu().numpy().tobytes() == orc.canonical(whole[start:end])
         asm.close()
         open(os.path.join(result_dir, f"rank{rank}"), "w").write("ok" if ok else "mismatch")
     finally:
