@@ -154,6 +154,20 @@ def cpu_roundtrip(sample_nt, min_seconds, min_reps, alphabet):
     }
 
 
+def cpu_baseline_leg(args, L):
+    """The `cpu_baseline` object of the GPU arm's line (guarded: never fatal)."""
+    sample = min(L, args.cpu_sample)
+    try:
+        r = cpu_roundtrip(sample, args.cpu_seconds, 5, args.alphabet)
+    except Exception as e:                  # noqa: BLE001
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed", "error": repr(e)}
+    return {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+            "sample": f"{sample} nt ({sample / GIB:.2f} GiB) of the workload x {r['reps']} reps, {r['variants']} "
+                      f"(AVX2 restatement of the reference's fastest variants; Rust crate not buildable here), "
+                      f"sharded by offset over {r['cores']} host threads, outputs pre-faulted",
+            "encode_nt_per_s": r["encode_nt_per_s"], "decode_nt_per_s": r["decode_nt_per_s"], "best": r["best"]}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -333,17 +347,19 @@ def run_gpu(args, rank, local_rank, world):
             assemble["fused_error"] = repr(e)
 
     # ---- e2e: host-slice C-ABI calls with pinned host buffers, copies inside the timed region ----------
-    e2e = None if args.no_e2e else run_e2e(args, cn, lib, _lib, torch, np, rank, local_rank, world, barrier, dev)
+    # auxiliary legs are guarded: a failure there (e.g. pinned-memory exhaustion) is reported inside the line, it must
+    # never cost the device-resident measurement above
+    e2e = None
+    if not args.no_e2e:
+        try:
+            e2e = run_e2e(args, cn, lib, _lib, torch, np, rank, local_rank, world, barrier, dev)
+        except Exception as e:              # noqa: BLE001
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "error": repr(e)}
 
     # ---- CPU baseline beside it (rank 0, N == 1 only) --------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_roundtrip(min(L, args.cpu_sample), args.cpu_seconds, 5, args.alphabet)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "sample": f"{min(L, args.cpu_sample)} nt ({min(L, args.cpu_sample) / GIB:.2f} GiB) of the workload x {r['reps']} reps, "
-                         f"{r['variants']} (AVX2 restatement of the reference's fastest variants; Rust crate not buildable here), "
-                         f"sharded by offset over {r['cores']} host threads, outputs pre-faulted",
-               "encode_nt_per_s": r["encode_nt_per_s"], "decode_nt_per_s": r["decode_nt_per_s"], "best": r["best"]}
+        cpu = cpu_baseline_leg(args, L)
 
     if rank != 0:
         return
