@@ -20,7 +20,7 @@ size_t g_host_small = (size_t)256 << 10;     // nucleotides at or below which th
 bool tuning_ok(int vec, int unroll, int threads)
 {
     return (vec == 16 || vec == 32) && (unroll == 1 || unroll == 2 || unroll == 4 || unroll == 8) &&
-           (threads == 128 || threads == 256 || threads == 512);
+           (threads == 64 || threads == 128 || threads == 256 || threads == 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -67,12 +67,14 @@ cudaError_t pick_threads(int threads, const A &a, cudaStream_t s)
 {
     if constexpr (ENC) {
         switch (threads) {
+        case 64:  return enc_launch<VEC, U, 64, false>(a, s);
         case 128: return enc_launch<VEC, U, 128, false>(a, s);
         case 512: return enc_launch<VEC, U, 512, false>(a, s);
         default:  return enc_launch<VEC, U, 256, false>(a, s);
         }
     } else {
         switch (threads) {
+        case 64:  return dec_launch<VEC, U, 64, false>(a, s);
         case 128: return dec_launch<VEC, U, 128, false>(a, s);
         case 512: return dec_launch<VEC, U, 512, false>(a, s);
         default:  return dec_launch<VEC, U, 256, false>(a, s);

@@ -133,7 +133,7 @@ CN_API int cn_time_decode_device(const void *d_bits, size_t nwords, size_t len, 
 /* ---- tuning knobs (defaults are the measured best on B200) ------------------------ */
 #define CN_DIR_ENCODE 0
 #define CN_DIR_DECODE 1
-/* vec: ASCII bytes per thread per memory instruction (16 or 32); unroll: 1,2,4,8; threads: 128,256,512 */
+/* vec: ASCII bytes per thread per memory instruction (16 or 32); unroll: 1,2,4,8; threads: 64,128,256,512 */
 CN_API int cn_set_tuning(int direction, int vec, int unroll, int threads);
 CN_API int cn_get_tuning(int direction, int *vec, int *unroll, int *threads);
 /* Host-slice strategy: 0 = staged (pinned ring + copy engines, chunked and overlapped),

@@ -19,7 +19,7 @@ with open(os.path.join(ROOT, "tests", "golden", "kat.json")) as f:
 
 SIZES = [1, 3, 4, 5, 15, 16, 17, 31, 32, 33, 47, 48, 49, 63, 64, 65, 127, 128, 129, 255, 1000, 4095, 4096, 4097,
          16383, 40000, 65536 + 17, (1 << 20), (1 << 20) + 17, 3 * (1 << 20) + 5]
-TUNINGS = [(v, u, t) for v in (16, 32) for u in (1, 2, 4, 8) for t in (128, 256, 512)]
+TUNINGS = [(v, u, t) for v in (16, 32) for u in (1, 2, 4, 8) for t in (64, 128, 256, 512)]
 
 
 @pytest.fixture(scope="module")

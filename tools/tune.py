@@ -29,7 +29,7 @@ ms = ctypes.c_float()
 results = []
 for vec in (16, 32):
     for unroll in (1, 2, 4, 8):
-        for threads in (128, 256, 512):
+        for threads in (64, 128, 256, 512):
             row = {"vec": vec, "unroll": unroll, "threads": threads}
             for name, d in (("encode", 0), ("decode", 1)):
                 _lib.check(lib.cn_set_tuning(d, vec, unroll, threads))
