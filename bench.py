@@ -356,6 +356,14 @@ def run_gpu(args, rank, local_rank, world):
         except Exception as e:              # noqa: BLE001
             e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "error": repr(e)}
 
+    # ---- extras (rank 0, N == 1): the widened rows measured the same way (CUDA events, device-resident) --------------
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            extras = run_extras(cn, torch, d_n, d_bits, d_out, L)
+        except Exception as e:              # noqa: BLE001
+            extras = {"error": repr(e)}
+
     # ---- CPU baseline beside it (rank 0, N == 1 only) --------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -400,7 +408,40 @@ def run_gpu(args, rank, local_rank, world):
     }
     if assemble:
         line["assemble"] = assemble
+    if extras:
+        line["extras"] = extras
     print(json.dumps(line), flush=True)
+
+
+def run_extras(cn, torch, d_n, d_bits, d_out, L, iters=20):
+    """Not part of `value`: the rows built after the 2-bit path on the same buffers.
+    checked encode = n_to_bits + count of invalid bytes in one pass; base-5 = n_to_bits2 / bits_to_n2 (27 nt per u64,
+    35/27 algorithmic bytes per nucleotide)."""
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    counter = torch.zeros(1, dtype=torch.int64, device=d_n.device)
+    ms_checked = timed(lambda: cn.encode_checked_device(d_n, counter, out=d_bits))
+    cn.generate2_device(d_n, 0, SEED, 12)                        # 5-letter data for the base-5 codec, same buffer
+    W2 = cn.words2_for_len(L)
+    d_bits2 = torch.empty(W2, dtype=torch.int64, device=d_n.device)
+    ms_e2 = timed(lambda: cn.encode2_device(d_n, out=d_bits2))
+    ms_d2 = timed(lambda: cn.decode2_device(d_bits2, L, out=d_out))
+    b2 = L + 8 * W2
+    return {
+        "encode_checked": {"ms": ms_checked, "gbs": BYTES_PER_NT * L / (ms_checked * 1e-3) / 1e9, "invalid_bytes_found": int(counter.item())},
+        "base5_encode": {"ms": ms_e2, "nt_per_s": L / (ms_e2 * 1e-3), "gbs": b2 / (ms_e2 * 1e-3) / 1e9},
+        "base5_decode": {"ms": ms_d2, "nt_per_s": L / (ms_d2 * 1e-3), "gbs": b2 / (ms_d2 * 1e-3) / 1e9},
+        "note": "device-resident, CUDA events, same 10 GiB buffers; not part of `value`",
+    }
 
 
 def verify(cn, torch, np, d_n, d_bits, d_out, L, offset, alphabet, in_place=False):
@@ -590,6 +631,7 @@ def main():
     ap.add_argument("--no-assemble", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-slice leg (profiling runs only)")
     ap.add_argument("--no-duplex", action="store_true", help="skip the two-thread pipelined e2e figure")
+    ap.add_argument("--no-extras", action="store_true", help="skip the checked-encode / base-5 extras")
     args = ap.parse_args()
 
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
