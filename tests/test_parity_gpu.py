@@ -506,3 +506,40 @@ def test_fuzz_sizes_and_alignments(cn, oracle, torch_cuda):
         canon = oracle.canonical2(host) if base5 else oracle.canonical(host)
         assert h[dst_off: dst_off + size].tobytes() == canon, (it, size, dst_off, base5)
         assert np.all(h[:dst_off] == 0x7E) and np.all(h[dst_off + size:] == 0x7E), (it, size, dst_off, base5)
+
+
+def test_device_calls_are_cuda_graph_capturable(cn, oracle, torch_cuda):
+    """cn_encode_device / cn_decode_device / cn_encode_checked_device / base-5 pair neither allocate nor synchronise:
+    a whole round trip can be captured once into a CUDA graph and replayed on new data (launch-bound small shards)."""
+    torch = torch_cuda
+    size = 40000 + 13                                             # the reference's bench size, ragged
+    d_n = torch.empty(size, dtype=torch.uint8, device="cuda")
+    d_bits = torch.empty(cn.words_for_len(size), dtype=torch.int64, device="cuda")
+    d_out = torch.empty(size, dtype=torch.uint8, device="cuda")
+    d_bits2 = torch.empty(cn.words2_for_len(size), dtype=torch.int64, device="cuda")
+    d_out2 = torch.empty(size, dtype=torch.uint8, device="cuda")
+    counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+    first = oracle.generate(size, seed=1, alphabet=10)
+    d_n.copy_(torch.from_numpy(first))
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                                 # warm-up outside capture
+        cn.encode_device(d_n, out=d_bits)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        cn.encode_checked_device(d_n, counter, out=d_bits)
+        cn.decode_device(d_bits, size, out=d_out)
+        cn.encode2_device(d_n, out=d_bits2)
+        cn.decode2_device(d_bits2, size, out=d_out2)
+    for seed in (2, 3, 4):
+        n = oracle.generate(size, seed=seed, alphabet=10)
+        n[seed] = ord("N")                                        # one invalid byte per replay
+        d_n.copy_(torch.from_numpy(n))
+        graph.replay()
+        torch.cuda.synchronize()
+        assert np.array_equal(d_bits.cpu().numpy().view(np.uint64), cn.n_to_bits_cuda(n))
+        assert d_out.cpu().numpy().tobytes() == cn.bits_to_n_cuda(cn.n_to_bits_cuda(n), size)
+        assert np.array_equal(d_bits2.cpu().numpy().view(np.uint64), oracle.n_to_bits2(n, "lut"))
+        assert d_out2.cpu().numpy().tobytes() == oracle.canonical2(n)
+    assert int(counter.item()) == 3
