@@ -13,7 +13,8 @@ data-path collective).  `e2e` = the same round trip through the host-slice C-ABI
 
 `--impl reference` times the reference's own fastest CPU variants (n_to_bits_movemask + bits_to_n_shuffle,
 restated in C because the Rust crate cannot be built here: no rustc/cargo) on all host cores.
-The oracle is loaded ONLY for the cpu_baseline / reference legs and the post-run verification.
+The oracle is loaded ONLY for the cpu_baseline / reference legs; the post-run verification of the timed outputs
+is an independent torch computation.
 """
 from __future__ import annotations
 
@@ -445,27 +446,30 @@ def run_extras(cn, torch, d_n, d_bits, d_out, L, iters=20):
 
 
 def verify(cn, torch, np, d_n, d_bits, d_out, L, offset, alphabet, in_place=False):
-    """decode(encode(x)) == canonical(x) over a 256 MiB prefix and the ragged end (device side), and a
-    4 MiB window of packed words bit-exact against the oracle's n_to_bits_lut of the host-generated data."""
-    import _oracle
-    orc = _oracle.Oracle()
-    lut = torch.zeros(256, dtype=torch.uint8, device=d_n.device)
+    """Post-run check of the timed outputs WITHOUT the oracle (the oracle is confined to the cpu_baseline / reference
+    legs and to tests/): (i) decode(encode(x)) == canonical(x) over a 256 MiB prefix and the ragged end, (ii) 4 MiB
+    windows of packed words equal an independent torch computation of the contract: code = (byte >> 1) & 3 for the
+    valid alphabet, nucleotide i at bits 2(i & 31) of word i >> 5 (src/n_to_bits.rs:39-42)."""
+    dev = d_n.device
+    lut = torch.zeros(256, dtype=torch.uint8, device=dev)
     for ch, canon in zip(b"ACGTUacgtu", b"ACGTTACGTT"):
         lut[ch] = canon
     ok = True
     span = min(L, 1 << 28)
+
+    def source(s, n):                       # the input window, regenerated when the round trip overwrote it in place
+        if in_place:
+            return cn.generate_device(torch.empty(n, dtype=torch.uint8, device=dev), offset + s, SEED, alphabet)
+        return d_n[s:s + n]
+
     for s in (0, L - span):
-        if in_place:        # d_n was overwritten by its canonical form: compare against the regenerated input
-            fresh = cn.generate_device(torch.empty(span, dtype=torch.uint8, device=d_n.device), offset + s, SEED, alphabet)
-            ok &= bool(torch.equal(d_out[s:s + span], lut[fresh.long()]))
-        else:
-            ok &= bool(torch.equal(d_out[s:s + span], lut[d_n[s:s + span].long()]))
-    win = min(L, 1 << 22)
+        ok &= bool(torch.equal(d_out[s:s + span], lut[source(s, span).long()]))
+    win = min(L, 1 << 22) & ~31
+    shifts = (torch.arange(32, device=dev, dtype=torch.int64) * 2)
     for s in (0, ((L - win) // 2) & ~31, (L - win) & ~31):
-        host = orc.generate(min(win, L - s), SEED, alphabet, offset=offset + s)
-        ref = orc.encode_mt(host, "lut")
-        got = d_bits[s // 32: s // 32 + ref.size].cpu().numpy().view(np.uint64)
-        ok &= bool(np.array_equal(got, ref))
+        codes = ((source(s, win).long() >> 1) & 3).view(-1, 32)
+        expect = (codes << shifts).sum(dim=1)                       # disjoint bit fields: sum == or; wraps into int64
+        ok &= bool(torch.equal(d_bits[s // 32: s // 32 + win // 32], expect))
     return ok
 
 

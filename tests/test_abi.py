@@ -76,3 +76,36 @@ def test_product_never_touches_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 text = open(os.path.join(dirpath, fn)).read()
                 assert "libcn_oracle" not in text and "cn_oracle" not in text and "oracle_" not in text, fn
+
+
+def test_oracle_is_confined_to_its_allowed_callers():
+    """Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may touch oracle/."""
+    import ast
+    offenders = []
+    for dirpath, dirnames, files in os.walk(ROOT):
+        dirnames[:] = [d for d in dirnames if d not in (".git", "tests", "oracle", "gpurun_out", "__pycache__", ".pytest_cache", ".hypothesis")]
+        for fn in files:
+            if not fn.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".rs")):
+                continue
+            path = os.path.join(dirpath, fn)
+            rel = os.path.relpath(path, ROOT)
+            text = open(path, errors="replace").read()
+            if "_oracle" not in text and "cn_oracle" not in text and "libcn_oracle" not in text:
+                continue
+            if rel == "bench.py":
+                tree = ast.parse(text)
+                for node in ast.walk(tree):
+                    if isinstance(node, ast.FunctionDef):
+                        uses = any(isinstance(n, ast.Import) and any(a.name == "_oracle" for a in n.names) for n in ast.walk(node))
+                        if uses and node.name not in ("cpu_roundtrip", "run_reference"):
+                            offenders.append(f"bench.py:{node.name}")
+            elif rel == "__graft_entry__.py":
+                tree = ast.parse(text)
+                for node in ast.walk(tree):
+                    if isinstance(node, ast.FunctionDef):
+                        uses = any(isinstance(n, ast.Import) and any(a.name == "_oracle" for a in n.names) for n in ast.walk(node))
+                        if uses and node.name != "smoke":
+                            offenders.append(f"__graft_entry__.py:{node.name}")
+            else:
+                offenders.append(rel)
+    assert offenders == [], offenders
