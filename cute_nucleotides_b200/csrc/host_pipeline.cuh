@@ -152,7 +152,13 @@ int pipe_prepare(HostPipe &p)
     int dev = 0;
     if (t_device >= 0) CN_CUDA(cudaSetDevice(t_device));
     CN_CUDA(cudaGetDevice(&dev));
-    if (p.ready && p.device == dev && p.chunk == g_host_chunk) return CN_OK;
+    if (p.ready && p.device == dev && p.chunk == g_host_chunk) {
+        // A previous call that failed half-way returned early and may have left slots marked busy with ITS destination
+        // offsets; never let them be retired into this call's buffers.  (Normally nothing is busy here.)
+        for (auto &sl : p.slot)
+            if (sl.busy) { cudaStreamSynchronize(sl.stream); cudaGetLastError(); sl.busy = false; sl.dst_bytes = 0; }
+        return CN_OK;
+    }
     p.destroy();
     p.device = dev;
     p.chunk = g_host_chunk;
