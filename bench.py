@@ -148,7 +148,19 @@ def cpu_roundtrip(sample_nt, min_seconds, min_reps, alphabet):
         t_enc.append(t1 - t0)
         t_dec.append(t2 - t1)
     step = [a + b for a, b in zip(t_enc, t_dec)]
+    # the reference as shipped is single-threaded: the same two variants on ONE thread, for context
+    one_enc, one_dec = [], []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        orc.encode_mt(n, enc_v, 1, out=words)
+        t1 = time.perf_counter()
+        orc.decode_mt(words, sample_nt, dec_v, 1, out=out)
+        t2 = time.perf_counter()
+        one_enc.append(t1 - t0)
+        one_dec.append(t2 - t1)
     return {
+        "single_thread": {"encode_nt_per_s": sample_nt / min(one_enc), "decode_nt_per_s": sample_nt / min(one_dec),
+                          "value": sample_nt / (min(one_enc) + min(one_dec))},
         "value": sample_nt / statistics.mean(step), "best": sample_nt / min(step), "reps": len(step),
         "encode_nt_per_s": sample_nt / statistics.mean(t_enc), "decode_nt_per_s": sample_nt / statistics.mean(t_dec),
         "cores": threads, "variants": f"n_to_bits_{enc_v} + bits_to_n_{dec_v}", "step_s": step,
@@ -166,7 +178,8 @@ def cpu_baseline_leg(args, L):
             "sample": f"{sample} nt ({sample / GIB:.2f} GiB) of the workload x {r['reps']} reps, {r['variants']} "
                       f"(AVX2 restatement of the reference's fastest variants; Rust crate not buildable here), "
                       f"sharded by offset over {r['cores']} host threads, outputs pre-faulted",
-            "encode_nt_per_s": r["encode_nt_per_s"], "decode_nt_per_s": r["decode_nt_per_s"], "best": r["best"]}
+            "encode_nt_per_s": r["encode_nt_per_s"], "decode_nt_per_s": r["decode_nt_per_s"], "best": r["best"],
+            "single_thread": r["single_thread"]}
 
 
 def run_reference(args, rank):
