@@ -23,7 +23,10 @@
  * cn_last_error() returns a thread-local description of the last failure on the calling thread.
  * Outputs are ALWAYS caller-allocated: no memory allocated here is ever handed to the caller to free
  * with a foreign allocator (Rust's Vec owns what Rust allocated).
- * All entry points are thread-safe; the host-slice calls keep per-thread staging state.
+ * All entry points are thread-safe; the host-slice calls keep per-thread staging state (released when the thread
+ * exits).  Input and output buffers of one call must not overlap (the reference's functions cannot alias either: they
+ * return a fresh Vec); decoding back over the buffer that was ENCODED earlier is fine (separate calls).
+ * The cn_set_* knobs are process-wide harness switches: set them before issuing calls, not concurrently with them.
  */
 #ifndef CUTE_NUCLEOTIDES_CUDA_H
 #define CUTE_NUCLEOTIDES_CUDA_H
