@@ -315,6 +315,15 @@ int encode2_device(const void *d_n, size_t len, void *d_out, cudaStream_t s)
         if (blocks > kMaxGrid) return fail(CN_ERR_ARG, "cn_encode2_device: input too large for one launch");
         if (g_b5_tma & 1) cn::b5_encode_kernel<true><<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(in, out, len, ntiles, total);
         else cn::b5_encode_kernel<false><<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(in, out, len, ntiles, total);
+    } else if ((addr(d_out) & 31) == 0) {
+        // ASCII side misaligned: shifted staging.  Only tiles whose trailing aligned vector lies inside the buffer.
+        const unsigned mis = (unsigned)(addr(d_n) & 15);
+        size_t ntiles = (len / 27) / cn::kB5WarpWords;
+        const size_t fit = len + mis >= 16 ? (len + mis - 16) / cn::kB5WarpBytes : 0;
+        if (fit < ntiles) ntiles = fit;
+        const size_t blocks = (ntiles + 1 + cn::kB5Warps - 1) / cn::kB5Warps;
+        if (blocks > kMaxGrid) return fail(CN_ERR_ARG, "cn_encode2_device: input too large for one launch");
+        cn::b5_encode_mis_kernel<<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(in, mis, out, len, ntiles, total);
     } else {
         size_t blocks = (total + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;
@@ -341,6 +350,12 @@ int decode2_device(const void *d_bits, size_t nwords, size_t len, void *d_out, c
         if (blocks > kMaxGrid) return fail(CN_ERR_ARG, "cn_decode2_device: input too large for one launch");
         if (g_b5_tma & 2) cn::b5_decode_kernel<true><<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(bits, out, len, ntiles, total);
         else cn::b5_decode_kernel<false><<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(bits, out, len, ntiles, total);
+    } else if ((addr(d_bits) & 31) == 0) {
+        const unsigned mis = (unsigned)(addr(d_out) & 15);      // ASCII side misaligned: shifted tile, byte stores at the edges
+        const size_t ntiles = (len / 27) / cn::kB5WarpWords;
+        const size_t blocks = (ntiles + 1 + cn::kB5Warps - 1) / cn::kB5Warps;
+        if (blocks > kMaxGrid) return fail(CN_ERR_ARG, "cn_decode2_device: input too large for one launch");
+        cn::b5_decode_mis_kernel<<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(bits, out, mis, len, ntiles, total);
     } else {
         size_t blocks = (total + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;

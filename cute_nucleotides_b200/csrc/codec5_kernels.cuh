@@ -233,6 +233,57 @@ b5_encode_kernel(const uint8_t *__restrict__ in, uint64_t *__restrict__ out, siz
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// encode, ASCII pointer NOT 16-byte aligned (mis = in & 15, 1..15).  TMA and 128-bit loads need aligned global
+// addresses, so the warp stages the 217 ALIGNED vectors that cover its tile; in shared memory the tile then starts
+// `mis` bytes in, i.e. each lane's 108 bytes start (mis & 3) bytes into a word: one more LDS and a funnel shift per
+// word, the shift amount the same for every lane.  The host only hands out tiles whose trailing vector lies inside
+// the buffer (ntiles * 3456 + 16 <= len + mis).
+// ------------------------------------------------------------------------------------------------------
+constexpr int kB5MisVecs = kB5WarpVecs + 1;                     // 217
+constexpr int kB5MisSmemPerWarp = kB5MisVecs * 16;              // 3472
+
+__global__ void __launch_bounds__(kB5Warps * 32)
+b5_encode_mis_kernel(const uint8_t *__restrict__ in, unsigned mis, uint64_t *__restrict__ out, size_t len, size_t ntiles,
+                     size_t total_words)
+{
+    __shared__ __align__(16) uint8_t smem[kB5Warps * kB5MisSmemPerWarp];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t g = (size_t)blockIdx.x * kB5Warps + warp;
+    if (g < ntiles) {
+        uint8_t *tile = smem + warp * kB5MisSmemPerWarp;
+        const uint8_t *src = (in - mis) + g * kB5WarpBytes;     // 16-byte aligned
+        uint4 v[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            unsigned i = lane + 32 * k;
+            if (i < kB5MisVecs) v[k] = ld_stream16(src + 16 * i);
+        }
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            unsigned i = lane + 32 * k;
+            if (i < kB5MisVecs) *reinterpret_cast<uint4 *>(tile + 16 * i) = v[k];
+        }
+        __syncwarp();
+        const uint32_t *tw = reinterpret_cast<const uint32_t *>(tile) + (mis >> 2) + 27 * lane;
+        const unsigned shift = (mis & 3u) * 8u;
+        uint32_t d[27];
+        uint32_t prev = tw[0];
+#pragma unroll
+        for (int k = 0; k < 27; k++) {
+            uint32_t next = tw[k + 1];
+            d[k] = b5_digits4(__funnelshift_r(prev, next, shift));
+            prev = next;
+        }
+        uint2 w[4];
+        b5_pack108(d, w);
+        st_stream32(out + g * kB5WarpWords + 4 * lane, make_uint4(w[0].x, w[0].y, w[1].x, w[1].y),
+                    make_uint4(w[2].x, w[2].y, w[3].x, w[3].y));
+    } else if (g == ntiles) {
+        b5_encode_scalar(in, len, out, ntiles * kB5WarpWords, total_words, lane, 32);
+    }
+}
+
 // generic encode for buffers the tiled kernel cannot take (ASCII pointer not 16-byte aligned)
 __global__ void __launch_bounds__(256)
 b5_encode_scalar_kernel(const uint8_t *__restrict__ in, uint64_t *__restrict__ out, size_t len, size_t total_words)
@@ -276,6 +327,55 @@ b5_decode_kernel(const uint64_t *__restrict__ bits, uint8_t *__restrict__ out, s
                 if (i < kB5WarpVecs) st_stream16(dst + 16 * i, *reinterpret_cast<const uint4 *>(tile + 16 * i));
             }
         }
+    } else if (g == ntiles) {
+        b5_decode_scalar(bits, out, len, ntiles * kB5WarpWords, total_words, lane, 32);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// decode, ASCII destination NOT 16-byte aligned (mis = out & 15).  The tile is laid out in shared memory `mis`
+// bytes in, so shared vector i corresponds to the ALIGNED global vector (out - mis) + 16 i: vectors 1..215 are
+// stored whole, the partial first and last vectors byte by byte (neighbouring tiles share those vectors and each
+// writes only its own bytes).  A lane's 108 bytes start (mis & 3) bytes into a word: the words are funnel-shifted
+// and the word straddling two lanes is completed with the next lane's first word (one shuffle).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kB5Warps * 32)
+b5_decode_mis_kernel(const uint64_t *__restrict__ bits, uint8_t *__restrict__ out, unsigned mis, size_t len, size_t ntiles,
+                     size_t total_words)
+{
+    __shared__ __align__(16) uint8_t smem[kB5Warps * kB5MisSmemPerWarp];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t g = (size_t)blockIdx.x * kB5Warps + warp;
+    if (g < ntiles) {
+        uint8_t *tile = smem + warp * kB5MisSmemPerWarp;
+        uint32_t *tw = reinterpret_cast<uint32_t *>(tile) + (mis >> 2) + 27 * lane;
+        const u32x8 w = ld_stream32(bits + g * kB5WarpWords + 4 * lane);
+        uint32_t a[4][7];
+#pragma unroll
+        for (int c = 0; c < 4; c++) b5_unpack27(make_uint2(w.v[2 * c], w.v[2 * c + 1]), a[c]);
+        uint32_t o[27];
+        b5_splice108(a, o);
+        const unsigned s = mis & 3u;
+        const uint32_t next0 = __shfl_down_sync(0xFFFFFFFFu, o[0], 1);
+        if (s == 0) {
+#pragma unroll
+            for (int k = 0; k < 27; k++) tw[k] = o[k];
+        } else {
+            const unsigned sh = 8u * (4u - s);                  // word k+1 = last s bytes of o[k], first 4-s bytes of o[k+1]
+            if (lane == 0) tw[0] = __funnelshift_r(0u, o[0], sh);
+#pragma unroll
+            for (int k = 0; k < 26; k++) tw[k + 1] = __funnelshift_r(o[k], o[k + 1], sh);
+            tw[27] = __funnelshift_r(o[26], next0, sh);         // lane 31: the extra bytes are past the tile, never stored
+        }
+        __syncwarp();
+        uint8_t *dst = (out - mis) + g * kB5WarpBytes;          // 16-byte aligned
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            unsigned i = lane + 32 * k;
+            if (i >= 1 && i < kB5MisVecs - 1) st_stream16(dst + 16 * i, *reinterpret_cast<const uint4 *>(tile + 16 * i));
+        }
+        if (lane < 16) { if (lane >= mis) dst[lane] = tile[lane]; }                                       // first, partial vector
+        else if (lane - 16 < mis) dst[16 * (kB5MisVecs - 1) + lane - 16] = tile[16 * (kB5MisVecs - 1) + lane - 16];   // last
     } else if (g == ntiles) {
         b5_decode_scalar(bits, out, len, ntiles * kB5WarpWords, total_words, lane, 32);
     }
