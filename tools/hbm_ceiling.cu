@@ -206,6 +206,33 @@ __global__ void __launch_bounds__(T) k_mix41_pf(const uint8_t *__restrict__ in, 
     for (int u = 0; u < U; u++) { size_t i = t + (size_t)u * T; if (i < nvec) st_stream8(out + (i << 1), v[u].v[0] ^ v[u].v[1] ^ v[u].v[2] ^ v[u].v[3], v[u].v[4] ^ v[u].v[5] ^ v[u].v[6] ^ v[u].v[7]); }
 }
 
+// decode-like and encode-like mixes with the CTA order remapped into S interleaved streams: CTA b works on tile
+// (b % S) * (nblocks / S) + b / S, so at any time the chip touches S far-apart regions instead of one linear front.
+template <int T>
+__global__ void __launch_bounds__(T) k_mix14_remap(const uint32_t *__restrict__ in, uint8_t *__restrict__ out, size_t nvec, unsigned S)
+{
+    const size_t per = gridDim.x / S;
+    const size_t tile = (size_t)(blockIdx.x % S) * per + blockIdx.x / S;
+    size_t i = tile * T + threadIdx.x;
+    if (blockIdx.x >= per * S) i = (size_t)blockIdx.x * T + threadIdx.x;
+    if (i < nvec) {
+        uint2 w = ld_stream8(in + (i << 1));
+        st_stream32(out + (i << 5), make_uint4(w.x, w.x + 1, w.x + 2, w.x + 3), make_uint4(w.y, w.y + 1, w.y + 2, w.y + 3));
+    }
+}
+template <int T>
+__global__ void __launch_bounds__(T) k_mix41_remap(const uint8_t *__restrict__ in, uint32_t *__restrict__ out, size_t nvec, unsigned S)
+{
+    const size_t per = gridDim.x / S;
+    const size_t tile = (size_t)(blockIdx.x % S) * per + blockIdx.x / S;
+    size_t i = tile * T + threadIdx.x;
+    if (blockIdx.x >= per * S) i = (size_t)blockIdx.x * T + threadIdx.x;
+    if (i < nvec) {
+        u32x8 v = ld_stream32(in + (i << 5));
+        st_stream8(out + (i << 1), v.v[0] ^ v.v[1] ^ v.v[2] ^ v.v[3], v.v[4] ^ v.v[5] ^ v.v[6] ^ v.v[7]);
+    }
+}
+
 // ---- TMA (cp.async.bulk) variants with the real codec arithmetic --------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
@@ -360,6 +387,12 @@ int main(int argc, char **argv)
             char var[96]; snprintf(var, sizeof var, "v32 u1 burst-prefetch G=%u (%.1f MB in) P=%u dist=1", G, G * 256 * 32 / 1e6, P);
             RUN("mix41_pf", var, 1.25 * L, (k_mix41_pf<1, 256><<<blocks_for(n32, 256), 256>>>(big, small, n32, G, P, 1)));
         }
+    }
+
+    for (unsigned S : {1u, 2u, 8u, 64u, 1024u}) {
+        char var[64]; snprintf(var, sizeof var, "v32 u1 CTA order remapped into %u streams", S);
+        RUN("mix14_remap", var, 1.25 * L, (k_mix14_remap<256><<<blocks_for(n32, 256), 256>>>(small, big, n32, S)));
+        RUN("mix41_remap", var, 1.25 * L, (k_mix41_remap<256><<<blocks_for(n32, 256), 256>>>(big, small, n32, S)));
     }
 
     // TMA variants (real arithmetic).  persistent grid: CTAS per SM x 148
