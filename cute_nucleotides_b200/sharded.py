@@ -10,17 +10,18 @@ from __future__ import annotations
 
 from typing import List, Tuple
 
-GRANULE = 32          # nucleotides per packed u64: shard boundaries must be multiples of this
+GRANULE = 32          # nucleotides per packed u64 of the 2-bit codec: shard boundaries must be multiples of this
+GROUP_2BIT, GROUP_BASE5 = 32, 27      # nucleotides per u64: n_to_bits (src/n_to_bits.rs:35) / n_to_bits2 (src/n_to_bits2.rs:38)
 
 
-def shard_bounds(total_len: int, world: int, rank: int, granule: int = GRANULE) -> Tuple[int, int]:
+def shard_bounds(total_len: int, world: int, rank: int, granule: int = GRANULE, group: int = GROUP_2BIT) -> Tuple[int, int]:
     """Contiguous range [start, end) of nucleotides owned by `rank`.
 
-    Boundaries are multiples of `granule` (itself a multiple of 32) so every rank writes whole, aligned words;
-    ranges are balanced to within one granule; the ragged global tail (total_len % 32) lands on the last
-    non-empty rank.  Ranks beyond the data get an empty range."""
-    if granule % GRANULE:
-        raise ValueError("granule must be a multiple of 32 nucleotides")
+    Boundaries are multiples of `granule` (itself a multiple of `group`, the nucleotides per packed word: 32 for the
+    2-bit codec, 27 for the base-5 codec) so every rank writes whole, aligned words; ranges are balanced to within one
+    granule; the ragged global tail lands on the last non-empty rank.  Ranks beyond the data get an empty range."""
+    if granule % group:
+        raise ValueError(f"granule must be a multiple of {group} nucleotides")
     if not 0 <= rank < world:
         raise ValueError("rank out of range")
     units = -(-total_len // granule)                       # ceil
@@ -32,21 +33,21 @@ def shard_bounds(total_len: int, world: int, rank: int, granule: int = GRANULE) 
     return start, end
 
 
-def all_bounds(total_len: int, world: int, granule: int = GRANULE) -> List[Tuple[int, int]]:
-    return [shard_bounds(total_len, world, r, granule) for r in range(world)]
+def all_bounds(total_len: int, world: int, granule: int = GRANULE, group: int = GROUP_2BIT) -> List[Tuple[int, int]]:
+    return [shard_bounds(total_len, world, r, granule, group) for r in range(world)]
 
 
-def words_for_len(length: int) -> int:
-    return (length >> 5) + (1 if length & 31 else 0)
+def words_for_len(length: int, group: int = GROUP_2BIT) -> int:
+    return length // group + (1 if length % group else 0)
 
 
-def word_bounds(total_len: int, world: int, rank: int, granule: int = GRANULE) -> Tuple[int, int]:
-    """Range of packed words produced by `rank` (start is exact because shard starts are multiples of 32)."""
-    start, end = shard_bounds(total_len, world, rank, granule)
-    return start >> 5, (start >> 5) + words_for_len(end - start)
+def word_bounds(total_len: int, world: int, rank: int, granule: int = GRANULE, group: int = GROUP_2BIT) -> Tuple[int, int]:
+    """Range of packed words produced by `rank` (start is exact because shard starts are multiples of `group`)."""
+    start, end = shard_bounds(total_len, world, rank, granule, group)
+    return start // group, start // group + words_for_len(end - start, group)
 
 
-def assemble_packed(local_words, total_len: int, group=None, granule: int = GRANULE):
+def assemble_packed(local_words, total_len: int, group=None, granule: int = GRANULE, codec_group: int = GROUP_2BIT):
     """All-gather the packed shards: every rank returns the full ceil(total_len/32)-word tensor.
 
     `local_words` is this rank's 8-byte-element tensor (CPU for gloo, CUDA for nccl) holding exactly the words
@@ -57,11 +58,11 @@ def assemble_packed(local_words, total_len: int, group=None, granule: int = GRAN
 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    spans = [word_bounds(total_len, world, r, granule) for r in range(world)]
+    spans = [word_bounds(total_len, world, r, granule, codec_group) for r in range(world)]
     counts = [e - s for s, e in spans]
     if local_words.numel() != counts[rank]:
         raise ValueError(f"rank {rank}: expected {counts[rank]} words, got {local_words.numel()}")
-    total_words = words_for_len(total_len)
+    total_words = words_for_len(total_len, codec_group)
     full = torch.empty(total_words, dtype=local_words.dtype, device=local_words.device)
     if len(set(counts)) == 1 and counts[0] * world == total_words:
         dist.all_gather_into_tensor(full, local_words.contiguous(), group=group)

@@ -31,6 +31,23 @@ def test_shard_bounds_cover_on_word_boundaries(total, world, granule):
     assert sum(e - s for s, e in words) == sharded.words_for_len(total)
 
 
+@pytest.mark.parametrize("total", [0, 1, 26, 27, 28, 1000, 40000, 27 * 4096 * 3 + 5, 10 * (1 << 30) + 21])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("granule", [27, 27 * 128, 27 * (1 << 15)])
+def test_shard_bounds_base5(total, world, granule):
+    """Same planner for the base-5 codec: boundaries on multiples of 27 nucleotides (whole words)."""
+    spans = sharded.all_bounds(total, world, granule, group=27)
+    assert spans[0][0] == 0 and spans[-1][1] == total
+    for (s0, e0), (s1, e1) in zip(spans, spans[1:]):
+        assert e0 == s1 and s0 <= e0
+    for s, e in spans:
+        assert s % 27 == 0 or s == total
+    words = [sharded.word_bounds(total, world, r, granule, group=27) for r in range(world)]
+    assert sum(e - s for s, e in words) == sharded.words_for_len(total, 27)
+    with pytest.raises(ValueError):
+        sharded.shard_bounds(total, world, 0, 32, group=27)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -59,6 +76,32 @@ def _worker(rank, world, port, total, granule, result_dir):
         open(os.path.join(result_dir, f"rank{rank}"), "w").write("ok" if ok else "mismatch")
     finally:
         dist.destroy_process_group()
+
+
+def _worker5(rank, world, port, total, granule, result_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        orc = _oracle.Oracle()
+        start, end = sharded.shard_bounds(total, world, rank, granule, group=27)
+        shard = orc.generate2(end - start, seed=9, alphabet=12, offset=start)
+        local = torch.from_numpy(orc.n_to_bits2(shard, "lut").view(np.int64).copy())
+        full = sharded.assemble_packed(local, total, granule=granule, codec_group=27)
+        whole = orc.n_to_bits2(orc.generate2(total, seed=9, alphabet=12), "lut")
+        ok = np.array_equal(full.numpy().view(np.uint64), whole)
+        open(os.path.join(result_dir, f"rank{rank}"), "w").write("ok" if ok else "mismatch")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_assemble_base5_world2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_worker5, args=(2, _free_port(), 27 * 5000 + 13, 27 * 64, str(tmp_path)), nprocs=2, join=True)
+    assert [open(tmp_path / f"rank{r}").read() for r in range(2)] == ["ok", "ok"]
 
 
 @pytest.mark.parametrize("total,granule", [(64 * 1000, 32), (100003, 32), ((1 << 21) + 77, 1 << 20), (31, 32)])
