@@ -247,7 +247,7 @@ int cn_set_tuning(int direction, int vec, int unroll, int threads)
 {
     if ((direction != CN_DIR_ENCODE && direction != CN_DIR_DECODE) || !tuning_ok(vec, unroll, threads))
         return fail(CN_ERR_ARG, "cn_set_tuning: unsupported (direction=%d vec=%d unroll=%d threads=%d)", direction, vec, unroll, threads);
-    g_tune[direction] = Tuning{vec, unroll, threads};
+    g_tune[direction].store(pack_tuning(vec, unroll, threads), std::memory_order_relaxed);
     return CN_OK;
 }
 
@@ -255,7 +255,8 @@ int cn_get_tuning(int direction, int *vec, int *unroll, int *threads)
 {
     if ((direction != CN_DIR_ENCODE && direction != CN_DIR_DECODE) || !vec || !unroll || !threads)
         return fail(CN_ERR_ARG, "cn_get_tuning: bad arguments");
-    *vec = g_tune[direction].vec; *unroll = g_tune[direction].unroll; *threads = g_tune[direction].threads;
+    const Tuning t = load_tuning(direction);
+    *vec = t.vec; *unroll = t.unroll; *threads = t.threads;
     return CN_OK;
 }
 

@@ -8,14 +8,21 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// tuning state (process-wide, set once by harnesses; plain loads on the hot path)
+// tuning state (process-wide harness knobs).  Each knob is ONE atomic word, so a call that races with a
+// cn_set_* sees either the old or the new setting, never a torn one; every call snapshots what it needs once.
 // ------------------------------------------------------------------------------------------------
 struct Tuning { int vec, unroll, threads; };
+constexpr uint32_t pack_tuning(int vec, int unroll, int threads) { return (uint32_t)vec | ((uint32_t)unroll << 8) | ((uint32_t)threads << 16); }
 // measured best on B200 (profiles/tune_r01.jsonl): 256-bit accesses, one vector per thread, 256 threads
-Tuning g_tune[2] = {{32, 1, 256}, {32, 1, 256}};
-int g_host_strategy = 0;
-size_t g_host_chunk = (size_t)16 << 20;      // ASCII bytes per pipeline chunk
-size_t g_host_small = (size_t)256 << 10;     // nucleotides at or below which the single-launch path is used
+std::atomic<uint32_t> g_tune[2] = {{pack_tuning(32, 1, 256)}, {pack_tuning(32, 1, 256)}};
+inline Tuning load_tuning(int direction)
+{
+    const uint32_t v = g_tune[direction].load(std::memory_order_relaxed);
+    return Tuning{(int)(v & 0xFF), (int)((v >> 8) & 0xFF), (int)(v >> 16)};
+}
+std::atomic<int> g_host_strategy{0};
+std::atomic<size_t> g_host_chunk{(size_t)16 << 20};      // ASCII bytes per pipeline chunk
+const size_t g_host_small = (size_t)256 << 10;           // nucleotides at or below which the single-launch path is used
 
 bool tuning_ok(int vec, int unroll, int threads)
 {
@@ -105,7 +112,7 @@ int encode_device(const void *d_n, size_t len, void *d_out, cudaStream_t s)
     if (len == 0) return CN_OK;
     if (!d_n || !d_out) return fail(CN_ERR_ARG, "cn_encode_device: null pointer");
     if (addr(d_out) & 7) return fail(CN_ERR_ARG, "cn_encode_device: output must be 8-byte aligned");
-    const Tuning t = g_tune[CN_DIR_ENCODE];
+    const Tuning t = load_tuning(CN_DIR_ENCODE);
     const size_t total32 = cn_words_for_len(len) * 2;          // output u32 units
     EncArgs a{};
     a.n0 = static_cast<const uint8_t *>(d_n);
@@ -261,7 +268,7 @@ int decode_device(const void *d_bits, size_t nwords, size_t len, void *d_out, cu
     if (len == 0) return CN_OK;
     if (!d_bits || !d_out) return fail(CN_ERR_ARG, "cn_decode_device: null pointer");
     if (addr(d_bits) & 7) return fail(CN_ERR_ARG, "cn_decode_device: packed input must be 8-byte aligned");
-    const Tuning t = g_tune[CN_DIR_DECODE];
+    const Tuning t = load_tuning(CN_DIR_DECODE);
     DecArgs a{};
     a.bits32 = static_cast<const uint32_t *>(d_bits);
     a.out0 = static_cast<uint8_t *>(d_out);

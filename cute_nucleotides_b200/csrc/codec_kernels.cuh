@@ -116,6 +116,31 @@ __device__ __forceinline__ void report_invalid(unsigned long long *counter, uint
     if (total && (threadIdx.x & 31) == 0) atomicAdd(counter, (unsigned long long)total);
 }
 
+// Exact per-byte version (slow path of the _lut-exact mode): 0x80 in every byte of x that is outside the alphabet.
+// The selector nibbles are masked to 3 bits, so no byte can influence its neighbour's lookup.
+__device__ __forceinline__ uint32_t invalid_bytes_mask(uint32_t x)
+{
+    uint32_t t = (x & 0x07070707u) | ((x >> 4) & 0x70707070u);            // byte0 = i0 | i1<<4, byte2 = i2 | i3<<4
+    uint32_t expect = prmt(0x40FF40FFu, 0x40FF5050u, __byte_perm(t, 0u, 0x4420));
+    uint32_t diff = (x & 0xD8D8D8D8u) ^ expect;
+    return (((diff & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | diff) & 0x80808080u;  // SWAR "byte != 0"
+}
+// n_to_bits_lut semantics (BYTE_LUT, src/n_to_bits.rs:8-21, :42): every byte outside the alphabet encodes as 0.
+// Clears bits 1..2 (the code bits) of the offending bytes so the ordinary pack then yields code 0 for them.
+__device__ __forceinline__ uint32_t lut_exact_clean(uint32_t x, uint32_t &n_invalid)
+{
+    const uint32_t bad = invalid_bytes_mask(x);
+    n_invalid += __popc(bad);
+    return x & ~((bad >> 5) | (bad >> 6));
+}
+
+// what the encode kernel does besides packing
+enum : int {
+    kEncPlain = 0,       // codes = (byte >> 1) & 3 for every byte, like the reference's SIMD encoders
+    kEncCount = 1,       // + count the bytes outside {A,C,G,T,U,a,c,g,t,u}
+    kEncLutExact = 2,    // bytes outside the alphabet encode as 0, exactly like n_to_bits_lut; counted too when a counter is given
+};
+
 // ------------------------------------------------------------------------------------------------
 // streaming loads / stores
 // ------------------------------------------------------------------------------------------------
@@ -173,6 +198,7 @@ __device__ __forceinline__ void st_stream32(void *p, const uint4 &a, const uint4
 
 // encode u32 units [first, total): unit u covers nucleotides 16u..16u+15, zero-padded beyond len
 // (the zero padding is the "unused high bits of the last word are zero" rule, n_to_bits.rs:35).
+template <bool LUT_EXACT = false>
 __device__ __forceinline__ uint32_t encode_edge(const uint8_t *__restrict__ n, size_t len,
                                                 uint32_t *__restrict__ out32, size_t first, size_t total, unsigned lane)
 {
@@ -184,8 +210,10 @@ __device__ __forceinline__ uint32_t encode_edge(const uint8_t *__restrict__ n, s
         for (int k = 0; k < 16; k++) {
             size_t i = base + k;
             uint32_t byte = (i < len) ? (uint32_t)n[i] : 0u;      // 0 -> code 0
+            const bool bad = i < len && invalid_byte(byte);
+            if (bad) invalid++;
+            if (LUT_EXACT && bad) byte = 0u;                      // BYTE_LUT: everything unlisted -> 0
             code |= ((byte >> 1) & 3u) << (2 * k);
-            if (i < len && invalid_byte(byte)) invalid++;
         }
         out32[u] = code;
     }
@@ -211,7 +239,7 @@ __device__ __forceinline__ void decode_edge(const uint32_t *__restrict__ bits32,
 //   nvec    : number of full VEC-byte groups the body covers
 //   edge_*  : the warp-sized ragged end, run by the last warp of the last CTA
 // ------------------------------------------------------------------------------------------------
-template <int VEC, int UNROLL, int THREADS, bool MISALIGN, bool CHECK = false>
+template <int VEC, int UNROLL, int THREADS, bool MISALIGN, int MODE = kEncPlain>
 __global__ void __launch_bounds__(THREADS)
 encode_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out32, size_t nvec,
               const uint8_t *__restrict__ n0, size_t len, size_t edge_first, size_t edge_total, unsigned shift_bytes,
@@ -221,13 +249,26 @@ encode_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out32, size
     constexpr size_t kTile = (size_t)THREADS * UNROLL;
     const size_t tile0 = (size_t)blockIdx.x * kTile;
     const size_t t = tile0 + threadIdx.x;
-    uint32_t n_invalid = 0;                // bytes outside the alphabet seen by this thread (CHECK, and the edge warp)
-    // CHECK: validate the registers that were just encoded; the exact count is only taken on a mismatch
+    uint32_t n_invalid = 0;                // bytes outside the alphabet seen by this thread (MODE != plain, and the edge warp)
+    // kEncCount: validate the registers that were just encoded; the exact count is only taken on a mismatch
     auto check16 = [&](uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-        if constexpr (CHECK) {
+        if constexpr (MODE == kEncCount) {
             uint32_t bad = invalid_accumulate(invalid_accumulate(invalid_accumulate(invalid_accumulate(0u, a), b), c), d);
             if (bad) n_invalid += count_invalid4(a) + count_invalid4(b) + count_invalid4(c) + count_invalid4(d);
         }
+    };
+    // 16 ASCII bytes -> one packed u32.  kEncLutExact: the cheap "anything invalid?" test runs on every register; only a
+    // thread that sees a hit takes the exact per-byte path that zeroes the offending codes (valid data pays nothing more
+    // than kEncCount does).
+    auto enc16 = [&](uint32_t a, uint32_t b, uint32_t c, uint32_t d) -> uint32_t {
+        if constexpr (MODE == kEncLutExact) {
+            uint32_t bad = invalid_accumulate(invalid_accumulate(invalid_accumulate(invalid_accumulate(0u, a), b), c), d);
+            if (bad) {
+                a = lut_exact_clean(a, n_invalid); b = lut_exact_clean(b, n_invalid);
+                c = lut_exact_clean(c, n_invalid); d = lut_exact_clean(d, n_invalid);
+            }
+        }
+        return pack16(a, b, c, d);
     };
 
     if constexpr (!MISALIGN) {
@@ -238,7 +279,7 @@ encode_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out32, size
                 for (int u = 0; u < UNROLL; u++) v[u] = ld_stream16(in + ((t + (size_t)u * THREADS) << 4));
 #pragma unroll
                 for (int u = 0; u < UNROLL; u++) {
-                    st_stream4(out32 + t + (size_t)u * THREADS, pack16(v[u]));
+                    st_stream4(out32 + t + (size_t)u * THREADS, enc16(v[u].x, v[u].y, v[u].z, v[u].w));
                     check16(v[u].x, v[u].y, v[u].z, v[u].w);
                 }
             } else {
@@ -248,8 +289,8 @@ encode_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out32, size
 #pragma unroll
                 for (int u = 0; u < UNROLL; u++) {
                     st_stream8(out32 + ((t + (size_t)u * THREADS) << 1),
-                               pack16(v[u].v[0], v[u].v[1], v[u].v[2], v[u].v[3]),
-                               pack16(v[u].v[4], v[u].v[5], v[u].v[6], v[u].v[7]));
+                               enc16(v[u].v[0], v[u].v[1], v[u].v[2], v[u].v[3]),
+                               enc16(v[u].v[4], v[u].v[5], v[u].v[6], v[u].v[7]));
                     check16(v[u].v[0], v[u].v[1], v[u].v[2], v[u].v[3]);
                     check16(v[u].v[4], v[u].v[5], v[u].v[6], v[u].v[7]);
                 }
@@ -261,12 +302,12 @@ encode_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out32, size
                 if (i < nvec) {
                     if constexpr (VEC == 16) {
                         uint4 v = ld_stream16(in + (i << 4));
-                        st_stream4(out32 + i, pack16(v));
+                        st_stream4(out32 + i, enc16(v.x, v.y, v.z, v.w));
                         check16(v.x, v.y, v.z, v.w);
                     } else {
                         u32x8 v = ld_stream32(in + (i << 5));
-                        st_stream8(out32 + (i << 1), pack16(v.v[0], v.v[1], v.v[2], v.v[3]),
-                                   pack16(v.v[4], v.v[5], v.v[6], v.v[7]));
+                        st_stream8(out32 + (i << 1), enc16(v.v[0], v.v[1], v.v[2], v.v[3]),
+                                   enc16(v.v[4], v.v[5], v.v[6], v.v[7]));
                         check16(v.v[0], v.v[1], v.v[2], v.v[3]);
                         check16(v.v[4], v.v[5], v.v[6], v.v[7]);
                     }
@@ -281,7 +322,9 @@ encode_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out32, size
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
             size_t i = t + (size_t)u * THREADS;
-            if (i < nvec) {
+            // group 0 would need the aligned vector that starts before the caller's buffer: the edge warp encodes it
+            // from the caller's own bytes instead, so nothing outside [n0, n0 + len) is ever read
+            if (i < nvec && i > 0) {
                 const uint4 *p = reinterpret_cast<const uint4 *>(in) + i;
                 uint4 a = __ldg(p), b = __ldg(p + 1);
                 uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -296,15 +339,18 @@ encode_kernel(const uint8_t *__restrict__ in, uint32_t *__restrict__ out32, size
                 }
                 const uint32_t y0 = __funnelshift_r(x[0], x[1], bit_off), y1 = __funnelshift_r(x[1], x[2], bit_off),
                                y2 = __funnelshift_r(x[2], x[3], bit_off), y3 = __funnelshift_r(x[3], x[4], bit_off);
-                st_stream4(out32 + i, pack16(y0, y1, y2, y3));
+                st_stream4(out32 + i, enc16(y0, y1, y2, y3));
                 check16(y0, y1, y2, y3);
             }
         }
     }
 
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x >= THREADS - 32)
-        n_invalid += encode_edge(n0, len, out32, edge_first, edge_total, threadIdx.x & 31);
-    if constexpr (CHECK) report_invalid(invalid_counter, n_invalid);
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x >= THREADS - 32) {
+        constexpr bool kExact = MODE == kEncLutExact;
+        if (MISALIGN && edge_first > 0) n_invalid += encode_edge<kExact>(n0, len, out32, 0, 1, threadIdx.x & 31);
+        n_invalid += encode_edge<kExact>(n0, len, out32, edge_first, edge_total, threadIdx.x & 31);
+    }
+    if constexpr (MODE != kEncPlain) { if (invalid_counter) report_invalid(invalid_counter, n_invalid); }
 }
 
 // ------------------------------------------------------------------------------------------------
