@@ -6,9 +6,18 @@ file); n_to_bits.py mirrors the reference's `n_to_bits` module; sharded.py is th
 from .n_to_bits import (  # noqa: F401
     LengthError, bits_to_n_cuda, decode_device, encode_checked_device, encode_device, generate_device,
     generate_words_device, n_to_bits_checked_cuda, n_to_bits_cuda, words_for_len,
+    ENC_COUNT, ENC_LUT_EXACT, ENC_PLAIN, encode_ex_device, n_to_bits_ex_cuda, n_to_bits_lut_cuda,
 )
 from .n_to_bits2 import (  # noqa: F401
     bits_to_n2_cuda, decode2_device, encode2_device, generate2_device, n_to_bits2_cuda, words2_for_len,
+    encode2_ex_device, n_to_bits2_ex_cuda, n_to_bits2_lut_cuda,
+)
+from .packed_ops import (  # noqa: F401
+    complement_cuda, complement_device, hamming_cuda, hamming_device, reverse_complement_cuda, reverse_complement_device,
+)
+from .multi import (  # noqa: F401
+    decode_sharded_devices, enable_peer_access, encode_gather_to_root, encode_sharded_devices, get_devices,
+    scatter_decode_from_root, set_devices, shard_bounds_c, synchronize_devices,
 )
 
 __version__ = "0.1.0"

@@ -14,7 +14,8 @@ LIB_PATH = os.environ.get("CN_CUDA_LIB", os.path.join(_HERE, "libcute_nucleotide
 
 CN_OK, CN_ERR_LENGTH, CN_ERR_CUDA, CN_ERR_ARG, CN_ERR_NOMEM = 0, 1, 2, 3, 4
 CN_DIR_ENCODE, CN_DIR_DECODE = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
+CN_ENC_PLAIN, CN_ENC_COUNT, CN_ENC_LUT_EXACT = 0, 1, 2
 
 # name -> (restype, argtypes); mirrors include/cute_nucleotides_cuda.h one to one
 PROTOTYPES = {
@@ -35,6 +36,23 @@ PROTOTYPES = {
     "cn_ipc_close": (c_int, [c_void_p, c_size_t]),
     "cn_n_to_bits_checked_host": (c_int, [c_void_p, c_size_t, c_void_p, POINTER(c_uint64)]),
     "cn_encode_checked_device": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "cn_n_to_bits_ex_host": (c_int, [c_void_p, c_size_t, c_void_p, c_int, POINTER(c_uint64)]),
+    "cn_encode_ex_device": (c_int, [c_void_p, c_size_t, c_void_p, c_int, c_void_p, c_void_p]),
+    "cn_n_to_bits2_ex_host": (c_int, [c_void_p, c_size_t, c_void_p, c_int, POINTER(c_uint64)]),
+    "cn_encode2_ex_device": (c_int, [c_void_p, c_size_t, c_void_p, c_int, c_void_p, c_void_p]),
+    "cn_set_devices": (c_int, [POINTER(c_int), c_int]),
+    "cn_get_devices": (c_int, [POINTER(c_int), c_int, POINTER(c_int)]),
+    "cn_shard_bounds": (c_int, [c_size_t, c_int, c_int, c_size_t, POINTER(c_size_t), POINTER(c_size_t)]),
+    "cn_encode_sharded": (c_int, [c_int, POINTER(c_int), POINTER(c_void_p), POINTER(c_size_t), POINTER(c_void_p), POINTER(c_void_p)]),
+    "cn_decode_sharded": (c_int, [c_int, POINTER(c_int), POINTER(c_void_p), POINTER(c_size_t), POINTER(c_size_t), POINTER(c_void_p), POINTER(c_void_p)]),
+    "cn_enable_peer_access": (c_int, [POINTER(c_int), c_int]),
+    "cn_synchronize_devices": (c_int, [POINTER(c_int), c_int]),
+    "cn_hamming_device": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
+    "cn_complement_device": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
+    "cn_reverse_complement_device": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
+    "cn_hamming_host": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, POINTER(c_uint64)]),
+    "cn_complement_host": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p]),
+    "cn_reverse_complement_host": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p]),
     "cn_words2_for_len": (c_size_t, [c_size_t]),
     "cn_n_to_bits2_host": (c_int, [c_void_p, c_size_t, c_void_p]),
     "cn_bits_to_n2_host": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p]),
@@ -55,6 +73,8 @@ PROTOTYPES = {
     "cn_set_tuning": (c_int, [c_int, c_int, c_int, c_int]),
     "cn_get_tuning": (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "cn_set_host_strategy": (c_int, [c_int, c_size_t]),
+    "cn_set_host_chunks": (c_int, [c_size_t, c_size_t]),
+    "cn_set_host_threads": (c_int, [c_int]),
 }
 
 

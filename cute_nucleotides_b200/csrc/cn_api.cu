@@ -7,23 +7,37 @@
 //     fn(&[u8]) -> Vec<u64> / fn(&[u64], usize) -> Vec<u8> (src/n_to_bits.rs:34, :51); PCIe-bound, so it is a chunked
 //     pipeline that keeps both DMA directions and the kernel busy at once.
 // There is no CPU fallback anywhere in this library: without a CUDA device every call fails with CN_ERR_CUDA.
-#include "host_pipeline.cuh"
+#include "multi_device.cuh"
+#include "packed_ops.cuh"
 
 namespace {
 
 // internal stream + events for cn_time_*_device
 struct Timer {
+    int device = -1;
     cudaStream_t stream = nullptr;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
 };
 thread_local Timer t_timer;
 
+// The stream and events belong to ONE device: they are rebuilt when the calling thread's current device has changed.
+// The private stream has no ordering against whatever produced the buffers, so the device is drained first.
 int timer_prepare(Timer &t)
 {
-    if (t.stream) return CN_OK;
-    CN_CUDA(cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking));
-    CN_CUDA(cudaEventCreate(&t.t0));
-    CN_CUDA(cudaEventCreate(&t.t1));
+    int dev = 0;
+    CN_CUDA(cudaGetDevice(&dev));
+    if (t.stream && t.device != dev) {
+        cudaEventDestroy(t.t0); cudaEventDestroy(t.t1); cudaStreamDestroy(t.stream);
+        cudaGetLastError();
+        t = Timer{};
+    }
+    if (!t.stream) {
+        CN_CUDA(cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking));
+        CN_CUDA(cudaEventCreate(&t.t0));
+        CN_CUDA(cudaEventCreate(&t.t1));
+        t.device = dev;
+    }
+    CN_CUDA(cudaDeviceSynchronize());
     return CN_OK;
 }
 
@@ -80,13 +94,66 @@ int cn_n_to_bits_checked_host(const uint8_t *n, size_t len, uint64_t *out, uint6
     *invalid_count = 0;
     if (len == 0) return CN_OK;
     if (!n || !out) return fail(CN_ERR_ARG, "cn_n_to_bits_checked_host: null pointer");
-    return host_codec(kCodec2bit, true, n, reinterpret_cast<uint8_t *>(out), len, invalid_count);
+    return host_codec(kCodec2bit, true, n, reinterpret_cast<uint8_t *>(out), len, HostMode{cn::kEncCount, invalid_count});
 }
 
 int cn_encode_checked_device(const void *d_n, size_t len, void *d_out, void *d_invalid_count, void *stream)
 {
-    return encode_checked_device(d_n, len, d_out, d_invalid_count, static_cast<cudaStream_t>(stream));
+    return encode_device(d_n, len, d_out, cn::kEncCount, static_cast<unsigned long long *>(d_invalid_count), static_cast<cudaStream_t>(stream));
 }
+
+static int ex_host(const Codec &cd, const char *who, const uint8_t *n, size_t len, uint64_t *out, int mode, uint64_t *invalid_count)
+{
+    if (mode != CN_ENC_PLAIN && mode != CN_ENC_COUNT && mode != CN_ENC_LUT_EXACT) return fail(CN_ERR_ARG, "%s: bad mode %d", who, mode);
+    if (mode == CN_ENC_COUNT && !invalid_count) return fail(CN_ERR_ARG, "%s: CN_ENC_COUNT needs a counter", who);
+    if (invalid_count) *invalid_count = 0;
+    if (len == 0) return CN_OK;
+    if (!n || !out) return fail(CN_ERR_ARG, "%s: null pointer", who);
+    return host_codec(cd, true, n, reinterpret_cast<uint8_t *>(out), len, HostMode{mode, invalid_count});
+}
+int cn_n_to_bits_ex_host(const uint8_t *n, size_t len, uint64_t *out, int mode, uint64_t *invalid_count)
+{
+    return ex_host(kCodec2bit, "cn_n_to_bits_ex_host", n, len, out, mode, invalid_count);
+}
+int cn_n_to_bits2_ex_host(const uint8_t *n, size_t len, uint64_t *out, int mode, uint64_t *invalid_count)
+{
+    return ex_host(kCodecBase5, "cn_n_to_bits2_ex_host", n, len, out, mode, invalid_count);
+}
+int cn_encode_ex_device(const void *d_n, size_t len, void *d_out, int mode, void *d_invalid_count, void *stream)
+{
+    return encode_device(d_n, len, d_out, mode, static_cast<unsigned long long *>(d_invalid_count), static_cast<cudaStream_t>(stream));
+}
+int cn_encode2_ex_device(const void *d_n, size_t len, void *d_out, int mode, void *d_invalid_count, void *stream)
+{
+    return encode2_device(d_n, len, d_out, mode, static_cast<unsigned long long *>(d_invalid_count), static_cast<cudaStream_t>(stream));
+}
+
+int cn_set_devices(const int *devices, int count) { return set_devices(devices, count); }
+int cn_get_devices(int *devices, int capacity, int *count)
+{
+    if (!count || capacity < 0 || (capacity > 0 && !devices)) return fail(CN_ERR_ARG, "cn_get_devices: bad arguments");
+    const std::vector<int> devs = devices_snapshot();
+    *count = (int)devs.size();
+    for (int i = 0; i < capacity && i < (int)devs.size(); i++) devices[i] = devs[i];
+    return CN_OK;
+}
+int cn_shard_bounds(size_t total_len, int nshards, int shard, size_t granule, size_t *start, size_t *end)
+{
+    if (nshards < 1 || shard < 0 || shard >= nshards || granule == 0 || !start || !end) return fail(CN_ERR_ARG, "cn_shard_bounds: bad arguments");
+    shard_range(total_len, nshards, shard, granule, start, end);
+    return CN_OK;
+}
+int cn_encode_sharded(int nshards, const int *devices, const void *const *d_n, const size_t *lens, void *const *d_out, void *const *streams)
+{
+    return encode_sharded(nshards, devices, d_n, lens, d_out, streams, cn::kEncPlain, nullptr);
+}
+int cn_decode_sharded(int nshards, const int *devices, const void *const *d_bits, const size_t *nwords, const size_t *lens,
+                      void *const *d_out, void *const *streams)
+{
+    return decode_sharded(nshards, devices, d_bits, nwords, lens, d_out, streams);
+}
+int cn_enable_peer_access(const int *devices, int count) { return enable_peer_access(devices, count); }
+int cn_synchronize_devices(const int *devices, int count) { return synchronize_devices(devices, count); }
 
 int cn_encode_multi_device(const void *d_n, size_t len, void *const *d_outs, int nout, void *stream)
 {
@@ -98,13 +165,29 @@ int cn_ipc_close(void *d_ptr, size_t offset) { return ipc_close(d_ptr, offset); 
 
 int cn_encode_device(const void *d_n, size_t len, void *d_out, void *stream)
 {
-    return encode_device(d_n, len, d_out, static_cast<cudaStream_t>(stream));
+    return encode_device(d_n, len, d_out, cn::kEncPlain, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int cn_decode_device(const void *d_bits, size_t nwords, size_t len, void *d_out, void *stream)
 {
     return decode_device(d_bits, nwords, len, d_out, static_cast<cudaStream_t>(stream));
 }
+
+int cn_hamming_device(const void *d_a, const void *d_b, size_t nwords, size_t len, void *d_result, void *stream)
+{
+    return hamming_device(d_a, d_b, nwords, len, d_result, static_cast<cudaStream_t>(stream));
+}
+int cn_complement_device(const void *d_bits, size_t nwords, size_t len, void *d_out, void *stream)
+{
+    return complement_device(d_bits, nwords, len, d_out, false, static_cast<cudaStream_t>(stream));
+}
+int cn_reverse_complement_device(const void *d_bits, size_t nwords, size_t len, void *d_out, void *stream)
+{
+    return complement_device(d_bits, nwords, len, d_out, true, static_cast<cudaStream_t>(stream));
+}
+int cn_hamming_host(const uint64_t *a, const uint64_t *b, size_t nwords, size_t len, uint64_t *result) { return hamming_host(a, b, nwords, len, result); }
+int cn_complement_host(const uint64_t *bits, size_t nwords, size_t len, uint64_t *out) { return complement_host(bits, nwords, len, out, false); }
+int cn_reverse_complement_host(const uint64_t *bits, size_t nwords, size_t len, uint64_t *out) { return complement_host(bits, nwords, len, out, true); }
 
 size_t cn_words2_for_len(size_t len) { return words2_for_len(len); }
 
@@ -125,7 +208,7 @@ int cn_bits_to_n2_host(const uint64_t *bits, size_t nwords, size_t len, uint8_t 
 
 int cn_encode2_device(const void *d_n, size_t len, void *d_out, void *stream)
 {
-    return encode2_device(d_n, len, d_out, static_cast<cudaStream_t>(stream));
+    return encode2_device(d_n, len, d_out, cn::kEncPlain, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int cn_decode2_device(const void *d_bits, size_t nwords, size_t len, void *d_out, void *stream)
@@ -213,10 +296,9 @@ int cn_time_encode_device(const void *d_n, size_t len, void *d_out, int iters, f
     Timer &t = t_timer;
     int rc = timer_prepare(t);
     if (rc != CN_OK) return rc;
-    CN_CUDA(cudaStreamSynchronize(t.stream));
     CN_CUDA(cudaEventRecord(t.t0, t.stream));
     for (int i = 0; i < iters; i++) {
-        rc = encode_device(d_n, len, d_out, t.stream);
+        rc = encode_device(d_n, len, d_out, cn::kEncPlain, nullptr, t.stream);
         if (rc != CN_OK) return rc;
     }
     CN_CUDA(cudaEventRecord(t.t1, t.stream));
@@ -231,7 +313,6 @@ int cn_time_decode_device(const void *d_bits, size_t nwords, size_t len, void *d
     Timer &t = t_timer;
     int rc = timer_prepare(t);
     if (rc != CN_OK) return rc;
-    CN_CUDA(cudaStreamSynchronize(t.stream));
     CN_CUDA(cudaEventRecord(t.t0, t.stream));
     for (int i = 0; i < iters; i++) {
         rc = decode_device(d_bits, nwords, len, d_out, t.stream);
@@ -267,8 +348,26 @@ int cn_set_host_strategy(int strategy, size_t chunk_bytes)
         if (chunk_bytes < 4096 || (chunk_bytes & 4095) || chunk_bytes > ((size_t)1 << 30))
             return fail(CN_ERR_ARG, "cn_set_host_strategy: chunk must be a multiple of 4096 in [4 KiB, 1 GiB]");
         g_host_chunk = chunk_bytes;
+        g_host_chunk_pageable = chunk_bytes;
     }
     g_host_strategy = strategy;
+    return CN_OK;
+}
+
+int cn_set_host_chunks(size_t pinned_chunk, size_t pageable_chunk)
+{
+    for (size_t c : {pinned_chunk, pageable_chunk})
+        if (c && (c < 4096 || (c & 4095) || c > ((size_t)1 << 30)))
+            return fail(CN_ERR_ARG, "cn_set_host_chunks: chunks must be multiples of 4096 in [4 KiB, 1 GiB]");
+    if (pinned_chunk) g_host_chunk = pinned_chunk;
+    if (pageable_chunk) g_host_chunk_pageable = pageable_chunk;
+    return CN_OK;
+}
+
+int cn_set_host_threads(int threads)
+{
+    if (threads < 0 || threads > 64) return fail(CN_ERR_ARG, "cn_set_host_threads: 0..64");
+    g_host_threads = threads;
     return CN_OK;
 }
 

@@ -107,12 +107,56 @@ inline Tuning narrow(Tuning t)
     return t;
 }
 
-int encode_device(const void *d_n, size_t len, void *d_out, cudaStream_t s)
+// encode + validation / _lut-exact semantics in one pass (fixed launch shapes: the measured-best ones for the kernel
+// that carries the extra ALU work)
+template <int VEC, int U, int T, bool MIS, int MODE>
+cudaError_t enc_launch_mode(const EncArgs &a, unsigned long long *counter, cudaStream_t s)
 {
+    size_t tile = (size_t)U * T;
+    size_t blocks = (a.nvec + tile - 1) / tile;
+    if (blocks == 0) blocks = 1;
+    if (blocks > kMaxGrid) return cudaErrorInvalidConfiguration;
+    cn::encode_kernel<VEC, U, T, MIS, MODE><<<(unsigned)blocks, T, 0, s>>>(a.in, a.out32, a.nvec, a.n0, a.len,
+                                                                          a.edge_first, a.edge_total, a.shift_bytes, counter);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+template <int MODE>
+cudaError_t enc_dispatch_mode(const EncArgs &a0, unsigned long long *counter, cudaStream_t s)
+{
+    EncArgs a = a0;
+    const unsigned mis = (unsigned)(addr(a.n0) & 15);
+    if (mis == 0) {
+        a.in = a.n0;
+        if ((addr(a.n0) & 31) == 0) {
+            a.nvec = a.len >> 5;
+            a.edge_first = a.nvec * 2;
+            // two vectors in flight per thread hide the extra ALU work: 1.845 ms vs 1.843 ms unchecked at 10 GiB
+            // (one vector per thread, the best shape for the plain kernel, costs +12 % here)
+            return enc_launch_mode<32, 2, 256, false, MODE>(a, counter, s);
+        }
+        a.nvec = a.len >> 4;
+        a.edge_first = a.nvec;
+        return enc_launch_mode<16, 4, 256, false, MODE>(a, counter, s);
+    }
+    size_t spans = (a.len + mis) >> 4;
+    a.in = a.n0 - mis;                 // rounded down to 16 B; the body never dereferences the vector that starts before n0
+    a.shift_bytes = mis;
+    a.nvec = spans > 0 ? spans - 1 : 0;
+    a.edge_first = a.nvec;
+    return enc_launch_mode<16, 4, 256, true, MODE>(a, counter, s);
+}
+
+// mode: cn::kEncPlain / kEncCount / kEncLutExact.  `counter` (device, 8-byte aligned) is incremented by the number of
+// bytes outside the alphabet in the non-plain modes; it may be null for kEncLutExact.
+int encode_device(const void *d_n, size_t len, void *d_out, int mode, unsigned long long *counter, cudaStream_t s)
+{
+    if (mode != cn::kEncPlain && mode != cn::kEncCount && mode != cn::kEncLutExact) return fail(CN_ERR_ARG, "encode: bad mode %d", mode);
+    if (mode == cn::kEncCount && !counter) return fail(CN_ERR_ARG, "cn_encode_checked_device: counter must be a non-null 8-byte aligned device pointer");
+    if (counter && (addr(counter) & 7)) return fail(CN_ERR_ARG, "encode: the invalid-byte counter must be 8-byte aligned");
     if (len == 0) return CN_OK;
     if (!d_n || !d_out) return fail(CN_ERR_ARG, "cn_encode_device: null pointer");
     if (addr(d_out) & 7) return fail(CN_ERR_ARG, "cn_encode_device: output must be 8-byte aligned");
-    const Tuning t = load_tuning(CN_DIR_ENCODE);
     const size_t total32 = cn_words_for_len(len) * 2;          // output u32 units
     EncArgs a{};
     a.n0 = static_cast<const uint8_t *>(d_n);
@@ -120,81 +164,34 @@ int encode_device(const void *d_n, size_t len, void *d_out, cudaStream_t s)
     a.out32 = static_cast<uint32_t *>(d_out);
     a.edge_total = total32;
     cudaError_t e;
-    const unsigned mis = (unsigned)(addr(d_n) & 15);
-    if (mis == 0) {
-        a.in = a.n0;
-        if (t.vec == 32 && (addr(d_n) & 31) == 0) {
-            a.nvec = len >> 5;
-            a.edge_first = a.nvec * 2;
-            e = pick_unroll<true, 32>(t, a, s);
+    if (mode == cn::kEncCount) e = enc_dispatch_mode<cn::kEncCount>(a, counter, s);
+    else if (mode == cn::kEncLutExact) e = enc_dispatch_mode<cn::kEncLutExact>(a, counter, s);
+    else {
+        const Tuning t = load_tuning(CN_DIR_ENCODE);
+        const unsigned mis = (unsigned)(addr(d_n) & 15);
+        if (mis == 0) {
+            a.in = a.n0;
+            if (t.vec == 32 && (addr(d_n) & 31) == 0) {
+                a.nvec = len >> 5;
+                a.edge_first = a.nvec * 2;
+                e = pick_unroll<true, 32>(t, a, s);
+            } else {
+                a.nvec = len >> 4;
+                a.edge_first = a.nvec;
+                e = pick_unroll<true, 16>(narrow(t), a, s);
+            }
         } else {
-            a.nvec = len >> 4;
+            // the body reads aligned vectors i and i+1 for group i >= 1, all inside [d_n, d_n + len); group 0 (whose first
+            // vector starts before d_n) is encoded from the caller's own bytes by the edge warp
+            size_t spans = (len + mis) >> 4;
+            a.in = a.n0 - mis;
+            a.shift_bytes = mis;
+            a.nvec = spans > 0 ? spans - 1 : 0;
             a.edge_first = a.nvec;
-            e = pick_unroll<true, 16>(narrow(t), a, s);
+            e = enc_launch<16, 4, 256, true>(a, s);
         }
-    } else {
-        // the body reads aligned vectors i and i+1 for group i; keep both inside [d_n, d_n + len)
-        size_t spans = (len + mis) >> 4;
-        a.in = a.n0 - mis;
-        a.shift_bytes = mis;
-        a.nvec = spans > 0 ? spans - 1 : 0;
-        a.edge_first = a.nvec;
-        e = enc_launch<16, 4, 256, true>(a, s);
     }
     if (e != cudaSuccess) return fail(CN_ERR_CUDA, "encode kernel launch failed: %s", cudaGetErrorString(e));
-    return CN_OK;
-}
-
-// encode + validation in one pass (fixed launch shapes: the measured-best ones for the checked kernel)
-template <int VEC, int U, int T, bool MIS>
-cudaError_t enc_launch_checked(const EncArgs &a, unsigned long long *counter, cudaStream_t s)
-{
-    size_t tile = (size_t)U * T;
-    size_t blocks = (a.nvec + tile - 1) / tile;
-    if (blocks == 0) blocks = 1;
-    if (blocks > kMaxGrid) return cudaErrorInvalidConfiguration;
-    cn::encode_kernel<VEC, U, T, MIS, true><<<(unsigned)blocks, T, 0, s>>>(a.in, a.out32, a.nvec, a.n0, a.len,
-                                                                          a.edge_first, a.edge_total, a.shift_bytes, counter);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return cudaGetLastError();
-}
-
-int encode_checked_device(const void *d_n, size_t len, void *d_out, void *d_invalid, cudaStream_t s)
-{
-    if (!d_invalid || (addr(d_invalid) & 7)) return fail(CN_ERR_ARG, "cn_encode_checked_device: counter must be a non-null 8-byte aligned device pointer");
-    if (len == 0) return CN_OK;
-    if (!d_n || !d_out) return fail(CN_ERR_ARG, "cn_encode_checked_device: null pointer");
-    if (addr(d_out) & 7) return fail(CN_ERR_ARG, "cn_encode_checked_device: output must be 8-byte aligned");
-    unsigned long long *counter = static_cast<unsigned long long *>(d_invalid);
-    EncArgs a{};
-    a.n0 = static_cast<const uint8_t *>(d_n);
-    a.len = len;
-    a.out32 = static_cast<uint32_t *>(d_out);
-    a.edge_total = cn_words_for_len(len) * 2;
-    cudaError_t e;
-    const unsigned mis = (unsigned)(addr(d_n) & 15);
-    if (mis == 0) {
-        a.in = a.n0;
-        if ((addr(d_n) & 31) == 0) {
-            a.nvec = len >> 5;
-            a.edge_first = a.nvec * 2;
-            // two vectors in flight per thread hide the extra ALU work: 1.845 ms vs 1.843 ms unchecked at 10 GiB
-            // (one vector per thread, the best shape for the plain kernel, costs +12 % here)
-            e = enc_launch_checked<32, 2, 256, false>(a, counter, s);
-        } else {
-            a.nvec = len >> 4;
-            a.edge_first = a.nvec;
-            e = enc_launch_checked<16, 4, 256, false>(a, counter, s);
-        }
-    } else {
-        size_t spans = (len + mis) >> 4;
-        a.in = a.n0 - mis;
-        a.shift_bytes = mis;
-        a.nvec = spans > 0 ? spans - 1 : 0;
-        a.edge_first = a.nvec;
-        e = enc_launch_checked<16, 4, 256, true>(a, counter, s);
-    }
-    if (e != cudaSuccess) return fail(CN_ERR_CUDA, "checked encode kernel launch failed: %s", cudaGetErrorString(e));
     return CN_OK;
 }
 
@@ -308,36 +305,48 @@ const int g_b5_tma = std::getenv("CN_B5_TMA") ? std::atoi(std::getenv("CN_B5_TMA
 
 inline size_t words2_for_len(size_t len) { return len / 27 + ((len % 27) ? 1 : 0); }
 
-int encode2_device(const void *d_n, size_t len, void *d_out, cudaStream_t s)
+template <int MODE>
+cudaError_t encode2_launch(const uint8_t *in, size_t len, uint64_t *out, unsigned long long *counter, cudaStream_t s)
 {
-    if (len == 0) return CN_OK;
-    if (!d_n || !d_out) return fail(CN_ERR_ARG, "cn_encode2_device: null pointer");
-    if (addr(d_out) & 7) return fail(CN_ERR_ARG, "cn_encode2_device: output must be 8-byte aligned");
     const size_t total = words2_for_len(len);
-    const uint8_t *in = static_cast<const uint8_t *>(d_n);
-    uint64_t *out = static_cast<uint64_t *>(d_out);
-    if ((addr(d_n) & 15) == 0 && (addr(d_out) & 31) == 0) {                  // 128-bit ASCII loads, 256-bit packed stores
+    if ((addr(in) & 15) == 0 && (addr(out) & 31) == 0) {                      // 128-bit ASCII loads, 256-bit packed stores
         const size_t ntiles = (len / 27) / cn::kB5WarpWords;                 // tiles of complete words
         const size_t blocks = (ntiles + 1 + cn::kB5Warps - 1) / cn::kB5Warps;
-        if (blocks > kMaxGrid) return fail(CN_ERR_ARG, "cn_encode2_device: input too large for one launch");
-        if (g_b5_tma & 1) cn::b5_encode_kernel<true><<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(in, out, len, ntiles, total);
-        else cn::b5_encode_kernel<false><<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(in, out, len, ntiles, total);
-    } else if ((addr(d_out) & 31) == 0) {
+        if (blocks > kMaxGrid) return cudaErrorInvalidConfiguration;
+        if (g_b5_tma & 1) cn::b5_encode_kernel<true, MODE><<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(in, out, len, ntiles, total, counter);
+        else cn::b5_encode_kernel<false, MODE><<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(in, out, len, ntiles, total, counter);
+    } else if ((addr(out) & 31) == 0) {
         // ASCII side misaligned: shifted staging.  Only tiles whose trailing aligned vector lies inside the buffer.
-        const unsigned mis = (unsigned)(addr(d_n) & 15);
+        const unsigned mis = (unsigned)(addr(in) & 15);
         size_t ntiles = (len / 27) / cn::kB5WarpWords;
         const size_t fit = len + mis >= 16 ? (len + mis - 16) / cn::kB5WarpBytes : 0;
         if (fit < ntiles) ntiles = fit;
         const size_t blocks = (ntiles + 1 + cn::kB5Warps - 1) / cn::kB5Warps;
-        if (blocks > kMaxGrid) return fail(CN_ERR_ARG, "cn_encode2_device: input too large for one launch");
-        cn::b5_encode_mis_kernel<<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(in, mis, out, len, ntiles, total);
+        if (blocks > kMaxGrid) return cudaErrorInvalidConfiguration;
+        cn::b5_encode_mis_kernel<MODE><<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(in, mis, out, len, ntiles, total, counter);
     } else {
         size_t blocks = (total + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;
-        cn::b5_encode_scalar_kernel<<<(unsigned)blocks, 256, 0, s>>>(in, out, len, total);
+        cn::b5_encode_scalar_kernel<MODE><<<(unsigned)blocks, 256, 0, s>>>(in, out, len, total, counter);
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    cudaError_t e = cudaGetLastError();
+    return cudaGetLastError();
+}
+
+// mode / counter as for encode_device; the alphabet here is {A,C,G,T,U,N} in either case
+int encode2_device(const void *d_n, size_t len, void *d_out, int mode, unsigned long long *counter, cudaStream_t s)
+{
+    if (mode != cn::kEncPlain && mode != cn::kEncCount && mode != cn::kEncLutExact) return fail(CN_ERR_ARG, "encode2: bad mode %d", mode);
+    if (mode == cn::kEncCount && !counter) return fail(CN_ERR_ARG, "cn_encode2_checked_device: counter must be a non-null 8-byte aligned device pointer");
+    if (counter && (addr(counter) & 7)) return fail(CN_ERR_ARG, "encode2: the invalid-byte counter must be 8-byte aligned");
+    if (len == 0) return CN_OK;
+    if (!d_n || !d_out) return fail(CN_ERR_ARG, "cn_encode2_device: null pointer");
+    if (addr(d_out) & 7) return fail(CN_ERR_ARG, "cn_encode2_device: output must be 8-byte aligned");
+    const uint8_t *in = static_cast<const uint8_t *>(d_n);
+    uint64_t *out = static_cast<uint64_t *>(d_out);
+    cudaError_t e = mode == cn::kEncCount      ? encode2_launch<cn::kEncCount>(in, len, out, counter, s)
+                    : mode == cn::kEncLutExact ? encode2_launch<cn::kEncLutExact>(in, len, out, counter, s)
+                                               : encode2_launch<cn::kEncPlain>(in, len, out, nullptr, s);
     if (e != cudaSuccess) return fail(CN_ERR_CUDA, "base-5 encode kernel launch failed: %s", cudaGetErrorString(e));
     return CN_OK;
 }
@@ -377,7 +386,7 @@ int decode2_device(const void *d_bits, size_t nwords, size_t len, void *d_out, c
 // What the host pipeline needs to know about a codec: nucleotides per word and the device entry points.
 struct Codec {
     unsigned group;                                                        // 32 (2-bit) or 27 (base-5)
-    int (*enc)(const void *, size_t, void *, cudaStream_t);
+    int (*enc)(const void *, size_t, void *, int mode, unsigned long long *counter, cudaStream_t);
     int (*dec)(const void *, size_t, size_t, void *, cudaStream_t);
     size_t words(size_t nt) const { return nt / group + ((nt % group) ? 1 : 0); }
 };

@@ -78,6 +78,46 @@ __device__ __forceinline__ uint32_t b5_digits4(uint32_t x)
     return __byte_perm(0x01000000u, 0x03040202u, sel);      // idx: 0,1(A),2 -> 0; 3(C) -> 1; 4(T),5(U) -> 2; 6(N) -> 4; 7(G) -> 3
 }
 
+// ---- validation fused into the base-5 encode (optional) ----------------------------------------------------
+// A byte belongs to {A,C,G,T,U,N,a,c,g,t,u,n} iff b & 0xD8 equals what its low 3 bits predict: a/c/g (1,3,7) -> 0x40,
+// t/u (4,5) -> 0x50, n (6) -> 0x48; indices 0 and 2 can never match.  The lookup reuses the PRMT selector b5_digits4
+// builds anyway (2 extra ALU ops per 4 nucleotides); the accumulated word is an exact "anything invalid in these
+// bytes?" flag (a byte >= 0x80 can also flag its neighbour, never hide itself), so a lane that sees it set recounts /
+// re-derives its bytes exactly.
+// exact: 0x80 in every byte of x outside the 12-letter alphabet
+__device__ __forceinline__ uint32_t b5_invalid_bytes_mask(uint32_t x)
+{
+    uint32_t t = (x & 0x07070707u) | ((x >> 4) & 0x70707070u);
+    uint32_t expect = prmt(0x40FF40FFu, 0x40485050u, __byte_perm(t, 0u, 0x4420));
+    uint32_t diff = (x & 0xD8D8D8D8u) ^ expect;
+    return (((diff & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | diff) & 0x80808080u;
+}
+__device__ __forceinline__ bool b5_invalid_byte(uint32_t b)
+{
+    uint32_t c = b | 0x20u;
+    return !(c == 'a' || c == 'c' || c == 'g' || c == 't' || c == 'u' || c == 'n');
+}
+// digits of 4 bytes under the given mode; in the non-plain modes `flag` accumulates the cheap any-invalid test
+template <int MODE>
+__device__ __forceinline__ uint32_t b5_digits4_mode(uint32_t x, uint32_t &flag)
+{
+    if constexpr (MODE == kEncPlain) return b5_digits4(x);
+    uint32_t t = (x & 0x87878787u) | ((x >> 4) & 0x78787878u);            // as in b5_digits4
+    uint32_t sel = __byte_perm(t, 0u, 0x4420);
+    flag |= (x & 0xD8D8D8D8u) ^ prmt(0x40FF40FFu, 0x40485050u, sel);
+    return __byte_perm(0x01000000u, 0x03040202u, sel);
+}
+// slow path of a lane whose flag fired: exact count, and (kEncLutExact) digit 0 for every byte outside the alphabet,
+// which is what BYTE_LUT of n_to_bits2_lut yields (src/n_to_bits2.rs:8-23)
+template <int MODE>
+__device__ __forceinline__ uint32_t b5_fix_digits4(uint32_t x, uint32_t d, uint32_t &n_invalid)
+{
+    const uint32_t bad = b5_invalid_bytes_mask(x);
+    n_invalid += __popc(bad);
+    if constexpr (MODE == kEncLutExact) d &= ~((bad >> 7) * 0xFFu);
+    return d;
+}
+
 // 108 digits (the bytes of d[0..26]) -> four packed words.  Triplet j sits at bytes 3j..3j+2; the pattern repeats
 // every 3 registers: offset 0 (product byte 2), 3 and 2 (funnel shift first), 1 (product byte 3).
 __device__ __forceinline__ void b5_pack108(const uint32_t (&d)[27], uint2 (&w)[4])
@@ -143,23 +183,33 @@ __device__ __forceinline__ void b5_splice108(const uint32_t (&a)[4][7], uint32_t
 // ---- scalar paths for whatever the warp tiles do not cover (ragged end, unaligned buffers) -------------
 __device__ __forceinline__ uint32_t b5_digit(uint32_t byte) { return (uint32_t)(0x0304020201000000ull >> (8 * (byte & 7))) & 7u; }
 
-// words [first, total): bytes past len count as digit 0 (src/n_to_bits2.rs:59-70)
-__device__ __forceinline__ void b5_encode_scalar(const uint8_t *__restrict__ n, size_t len, uint64_t *__restrict__ out,
-                                                 size_t first, size_t total, size_t lane, size_t stride)
+// words [first, total): bytes past len count as digit 0 (src/n_to_bits2.rs:59-70).  Returns the number of bytes outside
+// the alphabet among those this thread read (MODE != kEncPlain).
+template <int MODE = kEncPlain>
+__device__ __forceinline__ uint32_t b5_encode_scalar(const uint8_t *__restrict__ n, size_t len, uint64_t *__restrict__ out,
+                                                     size_t first, size_t total, size_t lane, size_t stride)
 {
+    uint32_t invalid = 0;
+    auto digit = [&](size_t i) -> uint32_t {
+        if (i >= len) return 0u;
+        const uint32_t byte = n[i];
+        if constexpr (MODE != kEncPlain) {
+            if (b5_invalid_byte(byte)) { invalid++; if (MODE == kEncLutExact) return 0u; }
+        }
+        return b5_digit(byte);
+    };
     for (size_t w = first + lane; w < total; w += stride) {
         uint64_t word = 0;
         size_t base = w * kB5Nt;
 #pragma unroll 1
         for (int t = 0; t < 9; t++) {
             size_t i = base + 3 * t;
-            uint32_t a = i < len ? b5_digit(n[i]) : 0u;
-            uint32_t b = i + 1 < len ? b5_digit(n[i + 1]) : 0u;
-            uint32_t c = i + 2 < len ? b5_digit(n[i + 2]) : 0u;
+            uint32_t a = digit(i), b = digit(i + 1), c = digit(i + 2);
             word |= (uint64_t)(a + 5 * b + 25 * c) << (7 * t);
         }
         out[w] = word;
     }
+    return invalid;
 }
 
 __device__ __forceinline__ void b5_decode_scalar(const uint64_t *__restrict__ bits, uint8_t *__restrict__ out, size_t len,
@@ -186,10 +236,12 @@ __device__ __forceinline__ void b5_decode_scalar(const uint64_t *__restrict__ bi
 // finishes words [ntiles*128, total_words) with the scalar path.  `in` must be 16-byte aligned when
 // ntiles > 0.
 // ------------------------------------------------------------------------------------------------------
-template <bool TMA>
+template <bool TMA, int MODE = kEncPlain>
 __global__ void __launch_bounds__(kB5Warps * 32)
-b5_encode_kernel(const uint8_t *__restrict__ in, uint64_t *__restrict__ out, size_t len, size_t ntiles, size_t total_words)
+b5_encode_kernel(const uint8_t *__restrict__ in, uint64_t *__restrict__ out, size_t len, size_t ntiles, size_t total_words,
+                 unsigned long long *__restrict__ invalid_counter)
 {
+    uint32_t n_invalid = 0;
     __shared__ __align__(128) uint8_t smem[kB5Warps * kB5SmemPerWarp];
     __shared__ uint64_t bars[kB5Warps];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -221,16 +273,23 @@ b5_encode_kernel(const uint8_t *__restrict__ in, uint64_t *__restrict__ out, siz
             __syncwarp();
         }
         const uint32_t *tw = reinterpret_cast<const uint32_t *>(tile) + 27 * lane;     // this lane's 108 bytes
-        uint32_t d[27];
+        uint32_t d[27], flag = 0;
 #pragma unroll
-        for (int k = 0; k < 27; k++) d[k] = b5_digits4(tw[k]);
+        for (int k = 0; k < 27; k++) d[k] = b5_digits4_mode<MODE>(tw[k], flag);
+        if constexpr (MODE != kEncPlain) {
+            if (flag) {                                          // rare: something in this lane's 108 bytes is off-alphabet
+#pragma unroll
+                for (int k = 0; k < 27; k++) d[k] = b5_fix_digits4<MODE>(tw[k], d[k], n_invalid);
+            }
+        }
         uint2 w[4];
         b5_pack108(d, w);
         st_stream32(out + g * kB5WarpWords + 4 * lane, make_uint4(w[0].x, w[0].y, w[1].x, w[1].y),
                     make_uint4(w[2].x, w[2].y, w[3].x, w[3].y));
     } else if (g == ntiles) {
-        b5_encode_scalar(in, len, out, ntiles * kB5WarpWords, total_words, lane, 32);
+        n_invalid += b5_encode_scalar<MODE>(in, len, out, ntiles * kB5WarpWords, total_words, lane, 32);
     }
+    if constexpr (MODE != kEncPlain) { if (invalid_counter) report_invalid(invalid_counter, n_invalid); }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -243,10 +302,12 @@ b5_encode_kernel(const uint8_t *__restrict__ in, uint64_t *__restrict__ out, siz
 constexpr int kB5MisVecs = kB5WarpVecs + 1;                     // 217
 constexpr int kB5MisSmemPerWarp = kB5MisVecs * 16;              // 3472
 
+template <int MODE = kEncPlain>
 __global__ void __launch_bounds__(kB5Warps * 32)
 b5_encode_mis_kernel(const uint8_t *__restrict__ in, unsigned mis, uint64_t *__restrict__ out, size_t len, size_t ntiles,
-                     size_t total_words)
+                     size_t total_words, unsigned long long *__restrict__ invalid_counter)
 {
+    uint32_t n_invalid = 0;
     __shared__ __align__(16) uint8_t smem[kB5Warps * kB5MisSmemPerWarp];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t g = (size_t)blockIdx.x * kB5Warps + warp;
@@ -257,7 +318,16 @@ b5_encode_mis_kernel(const uint8_t *__restrict__ in, unsigned mis, uint64_t *__r
 #pragma unroll
         for (int k = 0; k < 7; k++) {
             unsigned i = lane + 32 * k;
-            if (i < kB5MisVecs) v[k] = ld_stream16(src + 16 * i);
+            if (i < kB5MisVecs) {
+                if (g == 0 && i == 0) {
+                    // the first aligned vector starts `mis` bytes BEFORE the caller's buffer: take only the caller's bytes
+                    uint32_t w4[4] = {0u, 0u, 0u, 0u};
+                    for (unsigned b = mis; b < 16; b++) w4[b >> 2] |= (uint32_t)in[b - mis] << (8 * (b & 3));
+                    v[k] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                } else {
+                    v[k] = ld_stream16(src + 16 * i);
+                }
+            }
         }
 #pragma unroll
         for (int k = 0; k < 7; k++) {
@@ -267,28 +337,40 @@ b5_encode_mis_kernel(const uint8_t *__restrict__ in, unsigned mis, uint64_t *__r
         __syncwarp();
         const uint32_t *tw = reinterpret_cast<const uint32_t *>(tile) + (mis >> 2) + 27 * lane;
         const unsigned shift = (mis & 3u) * 8u;
-        uint32_t d[27];
+        uint32_t d[27], x[27], flag = 0;
         uint32_t prev = tw[0];
 #pragma unroll
         for (int k = 0; k < 27; k++) {
             uint32_t next = tw[k + 1];
-            d[k] = b5_digits4(__funnelshift_r(prev, next, shift));
+            x[k] = __funnelshift_r(prev, next, shift);
+            d[k] = b5_digits4_mode<MODE>(x[k], flag);
             prev = next;
+        }
+        if constexpr (MODE != kEncPlain) {
+            if (flag) {
+#pragma unroll
+                for (int k = 0; k < 27; k++) d[k] = b5_fix_digits4<MODE>(x[k], d[k], n_invalid);
+            }
         }
         uint2 w[4];
         b5_pack108(d, w);
         st_stream32(out + g * kB5WarpWords + 4 * lane, make_uint4(w[0].x, w[0].y, w[1].x, w[1].y),
                     make_uint4(w[2].x, w[2].y, w[3].x, w[3].y));
     } else if (g == ntiles) {
-        b5_encode_scalar(in, len, out, ntiles * kB5WarpWords, total_words, lane, 32);
+        n_invalid += b5_encode_scalar<MODE>(in, len, out, ntiles * kB5WarpWords, total_words, lane, 32);
     }
+    if constexpr (MODE != kEncPlain) { if (invalid_counter) report_invalid(invalid_counter, n_invalid); }
 }
 
 // generic encode for buffers the tiled kernel cannot take (ASCII pointer not 16-byte aligned)
+template <int MODE = kEncPlain>
 __global__ void __launch_bounds__(256)
-b5_encode_scalar_kernel(const uint8_t *__restrict__ in, uint64_t *__restrict__ out, size_t len, size_t total_words)
+b5_encode_scalar_kernel(const uint8_t *__restrict__ in, uint64_t *__restrict__ out, size_t len, size_t total_words,
+                        unsigned long long *__restrict__ invalid_counter)
 {
-    b5_encode_scalar(in, len, out, 0, total_words, (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
+    uint32_t n_invalid = b5_encode_scalar<MODE>(in, len, out, 0, total_words, (size_t)blockIdx.x * blockDim.x + threadIdx.x,
+                                                (size_t)gridDim.x * blockDim.x);
+    if constexpr (MODE != kEncPlain) { if (invalid_counter) report_invalid(invalid_counter, n_invalid); }
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -1,6 +1,14 @@
-// host_pipeline.cuh -- the host-slice path behind cn_n_to_bits_host / cn_bits_to_n_host (and the base-5 pair):
-// a process-wide pool of staging copier threads and a per-thread ring of {stream, event, pinned + device staging}
-// slots that keeps H2D copies, kernels and D2H copies of consecutive chunks in flight at once.
+// host_pipeline.cuh -- the host-slice path behind cn_n_to_bits_host / cn_bits_to_n_host (and the base-5 pair) on ONE
+// device: a process-wide pool of staging copier threads and a per-thread ring of {stream, event, pinned + device
+// staging} slots.  The calling thread only ISSUES work -- staging copies are posted to the pool and waited for when
+// their result is needed -- so for every chunk the copy into pinned staging, the H2D DMA, the kernel, the D2H DMA and
+// the copy out of staging all overlap with the neighbouring chunks'.  (multi_device.cuh fans one call out over
+// several of these pipelines, one per GPU.)
+//
+// What bounds this path was measured with tools/host_ceiling (profiles/host_ceiling_r02_*.jsonl): the PCIe link moves
+// 55 GB/s one way (45 + 45 both ways); cudaHostRegister of the caller's pages in place is NOT an alternative to staging
+// (4-8 GB/s on 4 KiB pages, does not scale over threads, and stalls a concurrent DMA stream to 1-4 GB/s); the staging
+// copies compete with the DMA engines for host memory bandwidth, which is why the copier count is bounded.
 #pragma once
 #include "cn_launch.cuh"
 
@@ -10,65 +18,134 @@
 #include <thread>
 #include <vector>
 #include <sys/mman.h>
+#include <immintrin.h>
 
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// staging copier.  Pageable caller memory cannot be DMA'd, so it is copied through pinned staging;
-// one thread moves ~10 GB/s (less into never-touched pages), PCIe Gen5 moves > 50 GB/s, so large
-// copies are cut into slices executed by a small process-wide pool (CN_HOST_THREADS, default
-// min(8, cores/2)) with the calling thread taking a slice too.  The pool is created on first use and
-// intentionally never destroyed (its threads only ever wait on a condition variable).
+// Copy flavours of the staging copier.  CN_HOST_COPY=nt selects non-temporal (streaming) stores: the destination is
+// written around the cache, which saves the read-for-ownership of every destination line.  Default: glibc memcpy,
+// which measured faster on the boxes profiled (tools/host_ceiling: 151 vs 121 GB/s of traffic on 8 threads).
 // ------------------------------------------------------------------------------------------------
+__attribute__((target("avx2"))) inline void copy_nt_avx2(uint8_t *dst, const uint8_t *src, size_t bytes)
+{
+    size_t head = (32 - (reinterpret_cast<uintptr_t>(dst) & 31)) & 31;
+    if (head > bytes) head = bytes;
+    memcpy(dst, src, head);
+    dst += head; src += head; bytes -= head;
+    const size_t body = bytes & ~(size_t)127;
+    for (size_t i = 0; i < body; i += 128) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 32));
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 64));
+        const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 96));
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 32), b);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 64), c);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 96), d);
+    }
+    _mm_sfence();
+    memcpy(dst + body, src + body, bytes - body);
+}
+const bool g_copy_nt = [] {
+    const char *env = std::getenv("CN_HOST_COPY");
+    return env && !strcmp(env, "nt") && __builtin_cpu_supports("avx2");
+}();
+inline void staging_copy(uint8_t *dst, const uint8_t *src, size_t bytes)
+{
+    if (g_copy_nt) copy_nt_avx2(dst, src, bytes);
+    else memcpy(dst, src, bytes);
+}
+
+// ------------------------------------------------------------------------------------------------
+// staging copier.  Pageable caller memory cannot be DMA'd, so it is copied through pinned staging by a small
+// process-wide pool (CN_HOST_THREADS / cn_set_host_threads, default min(8, cores/2) including the caller).
+// post() queues the slices of one copy and returns at once; wait() blocks until they are done and lets the
+// waiting thread execute queued slices itself.  The pool is created on first use and intentionally never
+// destroyed (its threads only ever wait on a condition variable).
+// ------------------------------------------------------------------------------------------------
+std::atomic<int> g_host_threads{0};          // 0: default
+
 class CopyPool {
 public:
+    struct Job { int pending = 0; };         // guarded by the pool mutex
+
     static CopyPool &get()
     {
         static CopyPool *pool = new CopyPool();      // leaked on purpose: no join at process exit
         return *pool;
     }
 
-    void copy(void *dst, const void *src, size_t bytes)
+    // queue dst <- src as slices of at most `slice` bytes
+    void post(Job &job, void *dst, const void *src, size_t bytes, size_t slice = kSlice)
     {
-        constexpr size_t kMinSlice = (size_t)256 << 10;
-        size_t parts = bytes / kMinSlice;
-        if (parts > threads_.size() + 1) parts = threads_.size() + 1;
-        if (parts <= 1) { memcpy(dst, src, bytes); return; }
-        const size_t slice = ((bytes / parts) + 4095) & ~(size_t)4095;
-        Job job;
-        size_t off = slice;                            // slice 0 is the caller's
+        if (bytes == 0) return;
+        ensure_threads();
         {
             std::lock_guard<std::mutex> lk(mu_);
-            while (off < bytes) {
+            for (size_t off = 0; off < bytes; off += slice) {
                 size_t n = bytes - off < slice ? bytes - off : slice;
                 queue_.push_back(Task{static_cast<uint8_t *>(dst) + off, static_cast<const uint8_t *>(src) + off, n, &job});
                 job.pending++;
-                off += n;
             }
         }
         cv_.notify_all();
-        memcpy(dst, src, slice < bytes ? slice : bytes);
-        std::unique_lock<std::mutex> lk(mu_);
-        job.done_cv.wait(lk, [&] { return job.pending == 0; });
     }
 
+    // returns when every slice posted on `job` has been copied; the caller copies slices too while it waits
+    void wait(Job &job)
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        while (job.pending > 0) {
+            if (!queue_.empty()) {
+                Task t = queue_.front();
+                queue_.pop_front();
+                lk.unlock();
+                staging_copy(t.dst, t.src, t.bytes);
+                lk.lock();
+                if (--t.job->pending == 0) done_cv_.notify_all();
+            } else {
+                done_cv_.wait(lk);
+            }
+        }
+    }
+
+    bool done(Job &job)
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        return job.pending == 0;
+    }
+
+    static constexpr size_t kSlice = (size_t)512 << 10;
+
 private:
-    struct Job { int pending = 0; std::condition_variable done_cv; };
     struct Task { uint8_t *dst; const uint8_t *src; size_t bytes; Job *job; };
 
-    CopyPool()
+    CopyPool() = default;
+
+    static int wanted_threads()
     {
-        int n = 0;
-        if (const char *env = std::getenv("CN_HOST_THREADS")) n = std::atoi(env) - 1;
-        else {
-            unsigned hc = std::thread::hardware_concurrency();
-            n = (int)(hc / 2 > 8 ? 8 : hc / 2) - 1;
+        int n = g_host_threads.load(std::memory_order_relaxed);
+        if (n <= 0) {
+            if (const char *env = std::getenv("CN_HOST_THREADS")) n = std::atoi(env);
         }
-        if (n < 0) n = 0;
-        if (n > 63) n = 63;
-        for (int i = 0; i < n; i++) {
-            threads_.emplace_back([this] { run(); });
-            threads_.back().detach();
+        if (n <= 0) {
+            unsigned hc = std::thread::hardware_concurrency();
+            n = (int)(hc / 2 > 8 ? 8 : hc / 2);
+        }
+        if (n < 1) n = 1;
+        if (n > 64) n = 64;
+        return n;
+    }
+    // the pool only ever grows: `n` copiers in total means n - 1 pool threads plus the waiting caller
+    void ensure_threads()
+    {
+        const int want = wanted_threads() - 1;
+        if (started_.load(std::memory_order_acquire) >= want) return;
+        std::lock_guard<std::mutex> lk(mu_);
+        while (started_.load(std::memory_order_relaxed) < want) {
+            std::thread([this] { run(); }).detach();
+            started_.fetch_add(1, std::memory_order_release);
         }
     }
     void run()
@@ -79,63 +156,66 @@ private:
             Task t = queue_.front();
             queue_.pop_front();
             lk.unlock();
-            memcpy(t.dst, t.src, t.bytes);
+            staging_copy(t.dst, t.src, t.bytes);
             lk.lock();
-            if (--t.job->pending == 0) t.job->done_cv.notify_all();
+            if (--t.job->pending == 0) done_cv_.notify_all();
         }
     }
     std::mutex mu_;
-    std::condition_variable cv_;
+    std::condition_variable cv_, done_cv_;
     std::deque<Task> queue_;
-    std::vector<std::thread> threads_;
+    std::atomic<int> started_{0};
 };
 
-inline void staged_copy(void *dst, const void *src, size_t bytes)
-{
-    if (bytes < ((size_t)512 << 10)) memcpy(dst, src, bytes);
-    else CopyPool::get().copy(dst, src, bytes);
-}
-
 // ------------------------------------------------------------------------------------------------
-// host-slice pipeline.  Per calling thread: kSlots slots, each with its own stream, a pinned and a
-// device staging buffer per direction.  Chunk c uses slot c % kSlots, so while chunk c's H2D copy
-// runs, chunk c-1's kernel and chunk c-2's D2H copy run on other streams/copy engines.
+// host-slice pipeline.  Per calling thread and device: kSlots slots, each with its own stream, a pinned and a
+// device staging buffer per direction.  Chunk c uses slot c % kSlots.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSlots = 4;
+constexpr int kSlots = 8;
+std::atomic<size_t> g_host_chunk_pageable{(size_t)4 << 20};   // ASCII bytes per chunk when a side of the call is pageable
 
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     uint8_t *pin_big = nullptr, *pin_small = nullptr;     // ASCII-sized / packed-sized pinned staging
     uint8_t *dev_big = nullptr, *dev_small = nullptr;
-    bool busy = false;
-    size_t dst_off = 0, dst_bytes = 0;                    // where the staged result goes once `done`
+    size_t pin_cap = 0, dev_cap = 0;                      // ASCII bytes the staging pairs were sized for
+    CopyPool::Job in_job, out_job;
+    bool in_posted = false, issued = false;
 };
 
 struct HostPipe {
     int device = -1;
-    size_t chunk = 0;
     Slot slot[kSlots];
-    unsigned long long *d_counter = nullptr;              // invalid-byte counter of the checked encode
+    unsigned long long *d_counter = nullptr;              // kSlots invalid-byte counters (one per slot stream)
+    unsigned long long *h_counter = nullptr;              // pinned landing area for them
     uint8_t *tiny_in = nullptr, *tiny_out = nullptr;      // pinned staging of the single-launch small-input path
     size_t tiny_bytes = 0;
     bool ready = false;
 
+    static void free_staging(Slot &sl)
+    {
+        if (sl.pin_big) cudaFreeHost(sl.pin_big);
+        if (sl.pin_small) cudaFreeHost(sl.pin_small);
+        if (sl.dev_big) cudaFree(sl.dev_big);
+        if (sl.dev_small) cudaFree(sl.dev_small);
+        sl.pin_big = sl.pin_small = sl.dev_big = sl.dev_small = nullptr;
+        sl.pin_cap = sl.dev_cap = 0;
+    }
     void destroy()
     {
         for (auto &sl : slot) {
-            if (sl.pin_big) cudaFreeHost(sl.pin_big);
-            if (sl.pin_small) cudaFreeHost(sl.pin_small);
-            if (sl.dev_big) cudaFree(sl.dev_big);
-            if (sl.dev_small) cudaFree(sl.dev_small);
+            free_staging(sl);
             if (sl.done) cudaEventDestroy(sl.done);
             if (sl.stream) cudaStreamDestroy(sl.stream);
-            sl = Slot{};
+            sl.done = nullptr;
+            sl.stream = nullptr;
         }
         if (d_counter) cudaFree(d_counter);
+        if (h_counter) cudaFreeHost(h_counter);
         if (tiny_in) cudaFreeHost(tiny_in);
         if (tiny_out) cudaFreeHost(tiny_out);
-        d_counter = nullptr;
+        d_counter = h_counter = nullptr;
         tiny_in = tiny_out = nullptr;
         ready = false;
     }
@@ -152,24 +232,18 @@ int pipe_prepare(HostPipe &p)
     int dev = 0;
     if (t_device >= 0) CN_CUDA(cudaSetDevice(t_device));
     CN_CUDA(cudaGetDevice(&dev));
-    if (p.ready && p.device == dev && p.chunk == g_host_chunk) {
-        // A previous call that failed half-way returned early and may have left slots marked busy with ITS destination
-        // offsets; never let them be retired into this call's buffers.  (Normally nothing is busy here.)
-        for (auto &sl : p.slot)
-            if (sl.busy) { cudaStreamSynchronize(sl.stream); cudaGetLastError(); sl.busy = false; sl.dst_bytes = 0; }
-        return CN_OK;
-    }
+    if (p.ready && p.device == dev) return CN_OK;
     p.destroy();
     p.device = dev;
-    p.chunk = g_host_chunk;
     // Only the cheap parts are created up front; the chunk-sized staging of a slot is allocated the first time a
-    // call needs it (slot_ensure), so a thread that only ever makes small calls pins 2 x 256 KiB, not 80 MiB.
+    // call needs it (slot_ensure), so a thread that only ever makes small calls pins 2 x 256 KiB, not hundreds of MiB.
     for (auto &sl : p.slot) {
         CN_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         CN_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
     }
     p.tiny_bytes = g_host_small + 64;
-    if (cudaMalloc(&p.d_counter, sizeof(unsigned long long)) != cudaSuccess ||
+    if (cudaMalloc(&p.d_counter, kSlots * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaHostAlloc(&p.h_counter, kSlots * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess ||
         cudaHostAlloc(&p.tiny_in, p.tiny_bytes, cudaHostAllocDefault) != cudaSuccess ||
         cudaHostAlloc(&p.tiny_out, p.tiny_bytes, cudaHostAllocDefault) != cudaSuccess) {
         cudaGetLastError();
@@ -180,23 +254,38 @@ int pipe_prepare(HostPipe &p)
     return CN_OK;
 }
 
-// chunk-sized staging of one slot, on first use: pinned buffers when a side of the call is pageable, device buffers
-// when the copy engines are used (strategy 0)
-int slot_ensure(HostPipe &p, Slot &sl, bool need_pinned, bool need_device)
+// Staging of one slot for chunks of up to `chunk` ASCII bytes, on first use or when a larger chunk size is asked for:
+// pinned buffers when a side of the call is pageable, device buffers when the copy engines are used (strategy 0).
+// Failure-atomic per pair: either both buffers of a pair exist with the recorded capacity, or neither does.
+int slot_ensure(Slot &sl, size_t chunk, bool need_pinned, bool need_device)
 {
-    const size_t big = p.chunk, small = p.chunk / 4 + 64;
-    if (need_pinned && !sl.pin_big) {
+    const size_t big = chunk, small = chunk / 4 + 64;
+    if (need_pinned && sl.pin_cap < chunk) {
+        if (sl.pin_big) cudaFreeHost(sl.pin_big);
+        if (sl.pin_small) cudaFreeHost(sl.pin_small);
+        sl.pin_big = sl.pin_small = nullptr;
+        sl.pin_cap = 0;
         if (cudaHostAlloc(&sl.pin_big, big, cudaHostAllocDefault) != cudaSuccess ||
             cudaHostAlloc(&sl.pin_small, small, cudaHostAllocDefault) != cudaSuccess) {
             cudaGetLastError();
+            if (sl.pin_big) cudaFreeHost(sl.pin_big);
+            sl.pin_big = sl.pin_small = nullptr;
             return fail(CN_ERR_NOMEM, "host pipeline: pinned staging allocation of %zu bytes failed", big + small);
         }
+        sl.pin_cap = chunk;
     }
-    if (need_device && !sl.dev_big) {
+    if (need_device && sl.dev_cap < chunk) {
+        if (sl.dev_big) cudaFree(sl.dev_big);
+        if (sl.dev_small) cudaFree(sl.dev_small);
+        sl.dev_big = sl.dev_small = nullptr;
+        sl.dev_cap = 0;
         if (cudaMalloc(&sl.dev_big, big) != cudaSuccess || cudaMalloc(&sl.dev_small, small) != cudaSuccess) {
             cudaGetLastError();
+            if (sl.dev_big) cudaFree(sl.dev_big);
+            sl.dev_big = sl.dev_small = nullptr;
             return fail(CN_ERR_NOMEM, "host pipeline: device staging allocation of %zu bytes failed", big + small);
         }
+        sl.dev_cap = chunk;
     }
     return CN_OK;
 }
@@ -214,71 +303,84 @@ bool is_pinned(const void *p, size_t bytes)
     return a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost;
 }
 
-// One implementation for both directions and both codecs: `big` is the ASCII side, `small` the packed side.
+// what a host-slice call asks of the encode kernel (decode ignores it)
+struct HostMode {
+    int enc_mode = cn::kEncPlain;          // kEncPlain / kEncCount / kEncLutExact (2-bit codec), or base-5 checked
+    uint64_t *invalid_out = nullptr;       // where the number of bytes outside the alphabet goes (may be null)
+};
+
+// One implementation for both directions and both codecs on ONE device: `big` is the ASCII side, `small` the packed side.
 //   encode: src = ASCII (len bytes)          dst = packed (8*words bytes)
 //   decode: src = packed (8*nwords bytes)    dst = ASCII (len bytes)
-int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, size_t len, uint64_t *invalid_out = nullptr)
+int host_codec_one(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, size_t len, const HostMode &mode)
 {
     HostPipe &p = t_pipe;
     int rc = pipe_prepare(p);
     if (rc != CN_OK) return rc;
+    CopyPool &pool = CopyPool::get();
 
     const size_t nwords = cd.words(len);
     const size_t src_bytes = encode ? len : nwords * 8;
     const size_t dst_bytes = encode ? nwords * 8 : len;
-    // Staging holds p.chunk ASCII bytes and p.chunk/4 (+64) packed bytes per slot; the base-5 codec packs
-    // 8 bytes per 27 nucleotides (> 1/4), so its chunks are 3/4 of the staging size.
-    const size_t max_nt = cd.group == 32 ? p.chunk : p.chunk / 4 * 3;
-    // checked encode (2-bit codec only): every chunk's kernel adds into one device counter, read back at the end
-    const bool checked = invalid_out != nullptr;
-    auto run_encode = [&](const void *in, size_t nt, void *out, cudaStream_t s) {
-        return checked ? encode_checked_device(in, nt, out, p.d_counter, s) : cd.enc(in, nt, out, s);
+    // every chunk's kernel adds into the counter of its slot; they are summed at the end
+    const bool counted = encode && mode.enc_mode != cn::kEncPlain;
+    auto run_encode = [&](const void *in, size_t nt, void *out, int slot, cudaStream_t s) {
+        return cd.enc(in, nt, out, mode.enc_mode, counted ? p.d_counter + slot : nullptr, s);
     };
-    auto finish_checked = [&]() -> int {
-        if (!checked) return CN_OK;
+    auto finish_counted = [&](int slots_used) -> int {
+        if (!counted) return CN_OK;
+        cudaStream_t s = p.slot[0].stream;               // every slot stream has been drained by now
+        CN_CUDA(cudaMemcpyAsync(p.h_counter, p.d_counter, slots_used * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CN_CUDA(cudaStreamSynchronize(s));
         unsigned long long v = 0;
-        CN_CUDA(cudaMemcpy(&v, p.d_counter, sizeof v, cudaMemcpyDeviceToHost));
-        *invalid_out = v;
+        for (int k = 0; k < slots_used; k++) v += p.h_counter[k];
+        if (mode.invalid_out) *mode.invalid_out = v;
         return CN_OK;
     };
-    if (checked) CN_CUDA(cudaMemset(p.d_counter, 0, sizeof(unsigned long long)));
 
     // Small inputs (the reference's own bench is 40 000 nt) are latency-bound: skip the pointer queries and
-    // the copy engines, stage through slot 0's pinned buffers and let ONE kernel read and write them in place
+    // the copy engines, stage through the small pinned buffers and let ONE kernel read and write them in place
     // over PCIe -- a single launch and a single synchronisation.
-    if (len <= g_host_small && len <= max_nt && src_bytes <= p.tiny_bytes && dst_bytes <= p.tiny_bytes) {
+    if (len <= g_host_small && src_bytes <= p.tiny_bytes && dst_bytes <= p.tiny_bytes) {
         Slot &sl = p.slot[0];
-        uint8_t *pin_in = p.tiny_in, *pin_out = p.tiny_out;
-        memcpy(pin_in, src, src_bytes);
-        rc = encode ? run_encode(pin_in, len, pin_out, sl.stream) : cd.dec(pin_in, nwords, len, pin_out, sl.stream);
-        if (rc != CN_OK) return rc;
+        if (counted) CN_CUDA(cudaMemsetAsync(p.d_counter, 0, sizeof(unsigned long long), sl.stream));
+        memcpy(p.tiny_in, src, src_bytes);
+        rc = encode ? run_encode(p.tiny_in, len, p.tiny_out, 0, sl.stream) : cd.dec(p.tiny_in, nwords, len, p.tiny_out, sl.stream);
+        if (rc != CN_OK) { cudaStreamSynchronize(sl.stream); cudaGetLastError(); return rc; }
         CN_CUDA(cudaStreamSynchronize(sl.stream));
-        memcpy(dst, pin_out, dst_bytes);
-        return finish_checked();
+        memcpy(dst, p.tiny_out, dst_bytes);
+        return finish_counted(1);
     }
 
     const bool src_pinned = is_pinned(src, src_bytes);
     const bool dst_pinned = is_pinned(dst, dst_bytes);
-    const bool zero_copy = g_host_strategy == 1;
+    const bool zero_copy = g_host_strategy.load(std::memory_order_relaxed) == 1;
 
     // zero-copy with both sides page-locked: a single kernel streams over PCIe in both directions
     if (zero_copy && src_pinned && dst_pinned) {
         cudaStream_t s = p.slot[0].stream;
-        rc = encode ? run_encode(src, len, dst, s) : cd.dec(src, nwords, len, dst, s);
-        if (rc != CN_OK) return rc;
+        if (counted) CN_CUDA(cudaMemsetAsync(p.d_counter, 0, sizeof(unsigned long long), s));
+        rc = encode ? run_encode(src, len, dst, 0, s) : cd.dec(src, nwords, len, dst, s);
+        if (rc != CN_OK) { cudaStreamSynchronize(s); cudaGetLastError(); return rc; }
         CN_CUDA(cudaStreamSynchronize(s));
-        return finish_checked();
+        return finish_counted(1);
     }
 
+    // Staging holds `stage` ASCII bytes and stage/4 (+64) packed bytes per slot; the base-5 codec packs 8 bytes per
+    // 27 nucleotides (> 1/4), so its chunks are 3/4 of the staging size.  Pinned callers are DMA'd in large chunks
+    // (fewer, longer transfers); pageable callers in small ones, so that a chunk is still in the CPU's last-level
+    // cache when the DMA engine reads it and many chunks are in flight at once.
+    const bool staged = !src_pinned || !dst_pinned;
+    const size_t stage = staged ? g_host_chunk_pageable.load(std::memory_order_relaxed) : g_host_chunk.load(std::memory_order_relaxed);
+    const size_t max_nt = cd.group == 32 ? stage : stage / 4 * 3;
     // Nucleotides per chunk: a multiple of `unit` (whole words, and whole warp tiles / 16-byte vectors where the
-    // staging size allows).  Mid-sized inputs are cut into ~8 chunks so that staging copies, both DMA directions
-    // and the kernel overlap; large inputs use the full staging size.
+    // staging size allows).  Mid-sized inputs are cut into ~2*kSlots chunks so that the stages overlap.
     size_t unit = cd.group == 32 ? 4096 : (size_t)cn::kB5WarpBytes;
     if (max_nt < unit) unit = cd.group;
     size_t chunk = max_nt / unit * unit;
-    if (len / 8 < chunk) {
-        size_t c8 = (len / 8 + unit - 1) / unit * unit;
-        size_t floor_nt = ((size_t)1 << 20) / unit * unit;
+    if (len / (2 * kSlots) < chunk) {
+        size_t c8 = (len / (2 * kSlots) + unit - 1) / unit * unit;
+        size_t floor_nt = ((size_t)512 << 10) / unit * unit;
         if (floor_nt == 0 || floor_nt > chunk) floor_nt = chunk;
         chunk = c8 < floor_nt ? floor_nt : (c8 < chunk ? c8 : chunk);
     }
@@ -288,63 +390,118 @@ int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, s
         const uintptr_t lo = (addr(dst) + 0x1FFFFF) & ~(uintptr_t)0x1FFFFF, hi = (addr(dst) + dst_bytes) & ~(uintptr_t)0x1FFFFF;
         if (hi > lo) (void)madvise(reinterpret_cast<void *>(lo), hi - lo, MADV_HUGEPAGE);
     }
-    size_t done_nt = 0;
-    int c = 0;
+
+    const size_t nchunks = (len + chunk - 1) / chunk;
+    const int slots_used = nchunks < (size_t)kSlots ? (int)nchunks : kSlots;
+    for (int k = 0; k < slots_used; k++) {
+        Slot &sl = p.slot[k];
+        rc = slot_ensure(sl, stage, staged, !zero_copy);
+        if (rc != CN_OK) return rc;
+        sl.in_posted = sl.issued = false;
+        if (counted) CN_CUDA(cudaMemsetAsync(p.d_counter + k, 0, sizeof(unsigned long long), sl.stream));
+    }
+
+    // geometry of chunk c
+    struct Geo { size_t nt, words, in_off, in_bytes, out_off, out_bytes; };
+    auto geo = [&](size_t c) {
+        Geo g;
+        const size_t first = c * chunk;
+        g.nt = len - first < chunk ? len - first : chunk;
+        g.words = cd.words(g.nt);
+        const size_t word_off = first / cd.group * 8;              // `first` is a multiple of the group size
+        g.in_off = encode ? first : word_off;
+        g.in_bytes = encode ? g.nt : g.words * 8;
+        g.out_off = encode ? word_off : first;
+        g.out_bytes = encode ? g.words * 8 : g.nt;
+        return g;
+    };
+    auto pin_in = [&](Slot &sl) { return encode ? sl.pin_big : sl.pin_small; };
+    auto pin_out = [&](Slot &sl) { return encode ? sl.pin_small : sl.pin_big; };
+
+    // The schedule, with S = kSlots (chunk k lives in slot k % S):
+    //   copy-in(k)  may start once the H2D copy of chunk k-S has finished        (chunk k-S retired)
+    //   issue(k)    = H2D + kernel + D2H + event, once copy-in(k) and copy-out(k-S) are done
+    //   copy-out(k) starts when chunk k is retired (its event has completed)
+    // in_next = chunks whose copy-in has been posted, issued = chunks submitted to the GPU, retired = chunks whose event
+    // has been waited for and whose copy-out has been posted; retired <= issued <= in_next <= retired + S.
+    size_t in_next = 0, issued = 0, retired = 0;
     int first_error = CN_OK;
-    while (done_nt < len) {
-        Slot &sl = p.slot[c % kSlots];
-        // retire whatever this slot was doing kSlots chunks ago
-        if (sl.busy) {
-            CN_CUDA(cudaEventSynchronize(sl.done));
-            if (sl.dst_bytes) staged_copy(dst + sl.dst_off, encode ? sl.pin_small : sl.pin_big, sl.dst_bytes);
-            sl.busy = false;
+    auto post_in = [&](size_t k) {
+        Slot &sl = p.slot[k % kSlots];
+        if (!src_pinned) { Geo g = geo(k); pool.post(sl.in_job, pin_in(sl), src + g.in_off, g.in_bytes); }
+        sl.in_posted = true;
+    };
+    auto retire = [&](size_t k) -> int {                              // wait for chunk k's DMA, start copying its result out
+        Slot &sl = p.slot[k % kSlots];
+        cudaError_t e = cudaEventSynchronize(sl.done);
+        sl.issued = false;
+        if (e != cudaSuccess) return fail(CN_ERR_CUDA, "host pipeline: chunk %zu failed: %s", k, cudaGetErrorString(e));
+        if (!dst_pinned) { Geo g = geo(k); pool.post(sl.out_job, dst + g.out_off, pin_out(sl), g.out_bytes); }
+        return CN_OK;
+    };
+    // retire, in order, every ISSUED chunk whose event has completed (block_first: wait for the oldest one)
+    auto retire_ready = [&](bool block_first) -> int {
+        while (retired < issued) {
+            if (!block_first && cudaEventQuery(p.slot[retired % kSlots].done) != cudaSuccess) { cudaGetLastError(); break; }
+            block_first = false;
+            int r = retire(retired);
+            retired++;
+            if (r != CN_OK) return r;
         }
-        rc = slot_ensure(p, sl, !src_pinned || !dst_pinned, !zero_copy);
-        if (rc != CN_OK) { first_error = rc; break; }
-        const size_t nt = (len - done_nt < chunk) ? len - done_nt : chunk;
-        const size_t words = cd.words(nt);
-        const size_t word_off = done_nt / cd.group * 8;             // done_nt is a multiple of the group size
-        const size_t in_off = encode ? done_nt : word_off;
-        const size_t in_bytes = encode ? nt : words * 8;
-        const size_t out_off = encode ? word_off : done_nt;
-        const size_t out_bytes = encode ? words * 8 : nt;
-        uint8_t *pin_in = encode ? sl.pin_big : sl.pin_small;
-        uint8_t *pin_out = encode ? sl.pin_small : sl.pin_big;
-        uint8_t *dev_in = encode ? sl.dev_big : sl.dev_small;
-        uint8_t *dev_out = encode ? sl.dev_small : sl.dev_big;
+        return CN_OK;
+    };
+    auto feed = [&] { while (in_next < nchunks && in_next < retired + kSlots) post_in(in_next++); };
 
-        const uint8_t *h_in = src + in_off;
-        if (!src_pinned) { staged_copy(pin_in, h_in, in_bytes); h_in = pin_in; }
-        uint8_t *h_out = dst_pinned ? dst + out_off : pin_out;
-
+    for (size_t k = 0; k < nchunks; k++) {
+        Slot &sl = p.slot[k % kSlots];
+        if ((rc = retire_ready(false)) != CN_OK) { first_error = rc; break; }
+        feed();
+        while (in_next <= k) {                                        // chunk k's slot still belongs to chunk k-S: wait for that one
+            if ((rc = retire_ready(true)) != CN_OK) { first_error = rc; break; }
+            feed();
+        }
+        if (first_error != CN_OK) break;
+        pool.wait(sl.in_job);                                         // chunk k is in pinned staging
+        pool.wait(sl.out_job);                                        // chunk k-S has left the slot's output staging
+        const Geo g = geo(k);
+        const uint8_t *h_in = src_pinned ? src + g.in_off : pin_in(sl);
+        uint8_t *h_out = dst_pinned ? dst + g.out_off : pin_out(sl);
+        const int slot_idx = (int)(k % kSlots);
+        cudaError_t e = cudaSuccess;
         if (zero_copy) {
             // kernel dereferences the pinned staging (or the caller's pinned side) directly
-            rc = encode ? run_encode(h_in, nt, h_out, sl.stream) : cd.dec(h_in, words, nt, h_out, sl.stream);
+            rc = encode ? run_encode(h_in, g.nt, h_out, slot_idx, sl.stream) : cd.dec(h_in, g.words, g.nt, h_out, sl.stream);
         } else {
-            CN_CUDA(cudaMemcpyAsync(dev_in, h_in, in_bytes, cudaMemcpyHostToDevice, sl.stream));
-            rc = encode ? run_encode(dev_in, nt, dev_out, sl.stream) : cd.dec(dev_in, words, nt, dev_out, sl.stream);
-            if (rc == CN_OK) CN_CUDA(cudaMemcpyAsync(h_out, dev_out, out_bytes, cudaMemcpyDeviceToHost, sl.stream));
+            uint8_t *dev_in = encode ? sl.dev_big : sl.dev_small, *dev_out = encode ? sl.dev_small : sl.dev_big;
+            e = cudaMemcpyAsync(dev_in, h_in, g.in_bytes, cudaMemcpyHostToDevice, sl.stream);
+            rc = e != cudaSuccess ? CN_OK
+                 : (encode ? run_encode(dev_in, g.nt, dev_out, slot_idx, sl.stream) : cd.dec(dev_in, g.words, g.nt, dev_out, sl.stream));
+            if (e == cudaSuccess && rc == CN_OK) e = cudaMemcpyAsync(h_out, dev_out, g.out_bytes, cudaMemcpyDeviceToHost, sl.stream);
         }
+        if (e == cudaSuccess && rc == CN_OK) e = cudaEventRecord(sl.done, sl.stream);
+        if (e != cudaSuccess) rc = fail(CN_ERR_CUDA, "host pipeline: submitting chunk %zu failed: %s", k, cudaGetErrorString(e));
         if (rc != CN_OK) { first_error = rc; break; }
-        CN_CUDA(cudaEventRecord(sl.done, sl.stream));
-        sl.busy = true;
-        sl.dst_off = out_off;
-        sl.dst_bytes = dst_pinned ? 0 : out_bytes;
-        done_nt += nt;
-        c++;
+        sl.issued = true;
+        issued = k + 1;
     }
-    // drain in submission order
-    for (int k = 0; k < kSlots; k++) {
-        Slot &sl = p.slot[(c + k) % kSlots];
-        if (!sl.busy) continue;
-        cudaError_t e = cudaEventSynchronize(sl.done);
-        if (e != cudaSuccess && first_error == CN_OK)
-            first_error = fail(CN_ERR_CUDA, "host pipeline drain failed: %s", cudaGetErrorString(e));
-        if (e == cudaSuccess && sl.dst_bytes) staged_copy(dst + sl.dst_off, encode ? sl.pin_small : sl.pin_big, sl.dst_bytes);
-        sl.busy = false;
+
+    // drain: wait for what is in flight, finish the copies (also on the error path: nothing may still be running into
+    // the caller's buffers, or out of staging a later call will reuse, when this call returns)
+    if (first_error == CN_OK) {
+        while (retired < nchunks) {
+            rc = retire(retired);
+            retired++;
+            if (rc != CN_OK) { first_error = rc; break; }
+        }
     }
-    if (first_error == CN_OK) first_error = finish_checked();
-    return first_error;
+    for (int k = 0; k < slots_used; k++) {
+        Slot &sl = p.slot[k];
+        if (first_error != CN_OK) { cudaStreamSynchronize(sl.stream); sl.issued = false; }
+        pool.wait(sl.in_job);
+        pool.wait(sl.out_job);
+    }
+    if (first_error != CN_OK) { cudaGetLastError(); return first_error; }
+    return finish_counted(slots_used);
 }
 
 }  // namespace

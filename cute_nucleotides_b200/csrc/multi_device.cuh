@@ -1,0 +1,296 @@
+// multi_device.cuh -- multi-GPU inside ONE process, behind the C ABI (SURVEY 8b `cn_encode_sharded`, 8e "single
+// process, one stream / host thread per GPU").
+//
+// The codec needs no exchange: packed word w depends only on nucleotides 32w..32w+31 (src/n_to_bits.rs:39-42), so a
+// call is cut into contiguous, word-aligned ranges and every range is an independent job for one GPU:
+//   * host-slice calls (cn_n_to_bits_host & co.): after cn_set_devices({d0..dn}) ONE call fans out over n GPUs --
+//     n PCIe links instead of one.  Each device has a persistent worker thread that owns a host_pipeline ring on its
+//     GPU; the calling thread runs the last range itself.  Nothing changes for the caller: same pointers, same result.
+//   * device-resident shards (cn_encode_sharded / cn_decode_sharded): one launch per device on that device's stream,
+//     no host thread needed (launches are asynchronous).  With cn_enable_peer_access a shard's output pointer may live
+//     on ANOTHER device -- the kernel's stores then travel over NVLink, which is the fused gather-to-root.
+#pragma once
+#include "host_pipeline.cuh"
+
+#include <map>
+
+namespace {
+
+// contiguous range [start, end) of shard `k` of `n`: boundaries are multiples of `granule`, ranges are balanced to
+// within one granule, the ragged tail lands on the last non-empty shard.  Same plan as sharded.shard_bounds (Python).
+inline void shard_range(size_t total, int n, int k, size_t granule, size_t *start, size_t *end)
+{
+    const size_t units = (total + granule - 1) / granule;
+    const size_t base = units / (size_t)n, extra = units % (size_t)n;
+    const size_t first = (size_t)k * base + ((size_t)k < extra ? (size_t)k : extra);
+    const size_t count = base + ((size_t)k < extra ? 1 : 0);
+    size_t s = first * granule, e = (first + count) * granule;
+    *start = s < total ? s : total;
+    *end = e < total ? e : total;
+}
+
+// ---- the device set of the host-slice calls -------------------------------------------------------------
+std::mutex g_devices_mu;
+std::vector<int> g_devices;                 // empty: single-device behaviour (the calling thread's device)
+bool g_devices_from_env_done = false;
+
+// CN_DEVICES=all | "0,1,2": lets an unmodified caller (the Rust shim, the C++ harness) fan out without code changes
+void devices_from_env_locked()
+{
+    if (g_devices_from_env_done) return;
+    g_devices_from_env_done = true;
+    const char *env = std::getenv("CN_DEVICES");
+    if (!env || !*env) return;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return; }
+    std::vector<int> devs;
+    if (!strcmp(env, "all")) {
+        for (int d = 0; d < count; d++) devs.push_back(d);
+    } else {
+        for (const char *p = env; *p;) {
+            char *endp = nullptr;
+            long d = strtol(p, &endp, 10);
+            if (endp == p) break;
+            if (d >= 0 && d < count) devs.push_back((int)d);
+            p = *endp == ',' ? endp + 1 : endp;
+        }
+    }
+    if (devs.size() > 1) g_devices = devs;
+}
+
+std::vector<int> devices_snapshot()
+{
+    std::lock_guard<std::mutex> lk(g_devices_mu);
+    devices_from_env_locked();
+    return g_devices;
+}
+
+int set_devices(const int *devices, int count)
+{
+    if (count < 0 || count > 64 || (count > 0 && !devices)) return fail(CN_ERR_ARG, "cn_set_devices: bad arguments");
+    int have = 0;
+    if (count > 0) CN_CUDA(cudaGetDeviceCount(&have));
+    std::vector<int> devs;
+    for (int i = 0; i < count; i++) {
+        if (devices[i] < 0 || devices[i] >= have) return fail(CN_ERR_ARG, "cn_set_devices: device %d out of range (0..%d)", devices[i], have - 1);
+        devs.push_back(devices[i]);
+    }
+    std::lock_guard<std::mutex> lk(g_devices_mu);
+    g_devices_from_env_done = true;          // an explicit call overrides CN_DEVICES
+    g_devices = devs;
+    return CN_OK;
+}
+
+// ---- per-device worker threads ----------------------------------------------------------------------------
+struct FanCall {                            // one fanned-out host-slice call
+    std::mutex mu;
+    std::condition_variable cv;
+    int pending = 0;
+};
+struct FanJob {
+    const Codec *cd = nullptr;
+    bool encode = false;
+    const uint8_t *src = nullptr;
+    uint8_t *dst = nullptr;
+    size_t len = 0;
+    int enc_mode = cn::kEncPlain;
+    bool counted = false;
+    uint64_t invalid = 0;
+    int rc = CN_OK;
+    char err[sizeof t_err] = "";
+    FanCall *call = nullptr;
+};
+
+int run_fan_job(FanJob &j, int device)
+{
+    const int saved = t_device;
+    t_device = device;
+    HostMode m;
+    m.enc_mode = j.enc_mode;
+    m.invalid_out = j.counted ? &j.invalid : nullptr;
+    j.rc = host_codec_one(*j.cd, j.encode, j.src, j.dst, j.len, m);
+    if (j.rc != CN_OK) { strncpy(j.err, t_err, sizeof j.err - 1); j.err[sizeof j.err - 1] = 0; }
+    t_device = saved;
+    return j.rc;
+}
+
+class DeviceWorker {
+public:
+    // one worker per device, created on first use, never destroyed (it only ever waits on a condition variable)
+    static DeviceWorker &get(int device)
+    {
+        static std::mutex mu;
+        static std::map<int, DeviceWorker *> *workers = new std::map<int, DeviceWorker *>();
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = workers->find(device);
+        if (it != workers->end()) return *it->second;
+        DeviceWorker *w = new DeviceWorker(device);
+        (*workers)[device] = w;
+        return *w;
+    }
+    void submit(FanJob *job)
+    {
+        { std::lock_guard<std::mutex> lk(mu_); queue_.push_back(job); }
+        cv_.notify_one();
+    }
+
+private:
+    explicit DeviceWorker(int device) : device_(device) { std::thread([this] { run(); }).detach(); }
+    void run()
+    {
+        for (;;) {
+            FanJob *job;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return !queue_.empty(); });
+                job = queue_.front();
+                queue_.pop_front();
+            }
+            run_fan_job(*job, device_);
+            FanCall *call = job->call;
+            { std::lock_guard<std::mutex> lk(call->mu); call->pending--; }
+            call->cv.notify_all();
+        }
+    }
+    const int device_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<FanJob *> queue_;
+};
+
+// below this many nucleotides per device a call is not worth splitting further
+constexpr size_t kFanMinPerDevice = (size_t)8 << 20;
+
+// The host-slice entry points land here: one device -> host_codec_one on the calling thread; a device set -> fan out.
+int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, size_t len, const HostMode &mode = HostMode{})
+{
+    if (mode.invalid_out) *mode.invalid_out = 0;
+    const std::vector<int> devs = devices_snapshot();
+    if (devs.empty()) return host_codec_one(cd, encode, src, dst, len, mode);
+
+    size_t parts = len / kFanMinPerDevice;
+    if (parts > devs.size()) parts = devs.size();
+    if (parts < 1) parts = 1;
+    // ranges are multiples of 1 Mi nucleotides (2-bit) / 256 warp tiles (base-5): whole words, whole chunk units, and
+    // 128-byte aligned packed offsets
+    const size_t granule = cd.group == 32 ? ((size_t)1 << 20) : (size_t)cn::kB5WarpBytes * 256;
+    int saved_dev = -1;
+    cudaGetDevice(&saved_dev);
+    cudaGetLastError();
+
+    std::vector<FanJob> jobs(parts);
+    FanCall call;
+    size_t live = 0;
+    for (size_t k = 0; k < parts; k++) {
+        size_t s, e;
+        shard_range(len, (int)parts, (int)k, granule, &s, &e);
+        FanJob &j = jobs[k];
+        j.cd = &cd; j.encode = encode; j.len = e - s; j.enc_mode = mode.enc_mode;
+        j.counted = encode && mode.enc_mode != cn::kEncPlain;
+        j.call = &call;
+        const size_t word_off = s / cd.group * 8;
+        j.src = src + (encode ? s : word_off);
+        j.dst = dst + (encode ? word_off : s);
+        if (j.len) live++;
+    }
+    // every range but the last goes to its device's worker; the calling thread runs the last one itself
+    call.pending = 0;
+    for (size_t k = 0; k + 1 < parts; k++)
+        if (jobs[k].len) call.pending++;
+    for (size_t k = 0; k + 1 < parts; k++)
+        if (jobs[k].len) DeviceWorker::get(devs[k]).submit(&jobs[k]);
+    if (jobs[parts - 1].len) run_fan_job(jobs[parts - 1], devs[parts - 1]);
+    {
+        std::unique_lock<std::mutex> lk(call.mu);
+        call.cv.wait(lk, [&] { return call.pending == 0; });
+    }
+    if (saved_dev >= 0) { cudaSetDevice(saved_dev); cudaGetLastError(); }
+    (void)live;
+    uint64_t invalid = 0;
+    for (FanJob &j : jobs) {
+        if (j.rc != CN_OK) { snprintf(t_err, sizeof t_err, "%s", j.err); return j.rc; }
+        invalid += j.invalid;
+    }
+    if (mode.invalid_out) *mode.invalid_out = invalid;
+    return CN_OK;
+}
+
+// ---- device-resident shards, one per device, single process ---------------------------------------------
+struct DeviceGuard {                        // launches happen on other devices; leave the caller's current device as it was
+    int saved = -1;
+    DeviceGuard() { if (cudaGetDevice(&saved) != cudaSuccess) { saved = -1; cudaGetLastError(); } }
+    ~DeviceGuard() { if (saved >= 0) { cudaSetDevice(saved); cudaGetLastError(); } }
+};
+
+int check_shard_args(const char *who, int nshards, const int *devices, const void *a, const void *b, const void *c)
+{
+    if (nshards < 1 || nshards > 64 || !devices || !a || !b || !c) return fail(CN_ERR_ARG, "%s: bad arguments", who);
+    return CN_OK;
+}
+
+int encode_sharded(int nshards, const int *devices, const void *const *d_n, const size_t *lens, void *const *d_out,
+                   void *const *streams, int mode, void *const *counters)
+{
+    int rc = check_shard_args("cn_encode_sharded", nshards, devices, d_n, lens, d_out);
+    if (rc != CN_OK) return rc;
+    DeviceGuard guard;
+    for (int k = 0; k < nshards; k++) {
+        if (lens[k] == 0) continue;
+        CN_CUDA(cudaSetDevice(devices[k]));
+        cudaStream_t s = streams ? static_cast<cudaStream_t>(streams[k]) : nullptr;
+        rc = encode_device(d_n[k], lens[k], d_out[k], mode, counters ? static_cast<unsigned long long *>(counters[k]) : nullptr, s);
+        if (rc != CN_OK) return rc;
+    }
+    return CN_OK;
+}
+
+int decode_sharded(int nshards, const int *devices, const void *const *d_bits, const size_t *nwords, const size_t *lens,
+                   void *const *d_out, void *const *streams)
+{
+    int rc = check_shard_args("cn_decode_sharded", nshards, devices, d_bits, lens, d_out);
+    if (rc != CN_OK) return rc;
+    if (!nwords) return fail(CN_ERR_ARG, "cn_decode_sharded: bad arguments");
+    for (int k = 0; k < nshards; k++)                                   // the reference's panic, before anything is launched
+        if (lens[k] > (nwords[k] << 5) || (nwords[k] >> 59) != 0) return fail(CN_ERR_LENGTH, "%s", kPanicText);
+    DeviceGuard guard;
+    for (int k = 0; k < nshards; k++) {
+        if (lens[k] == 0) continue;
+        CN_CUDA(cudaSetDevice(devices[k]));
+        cudaStream_t s = streams ? static_cast<cudaStream_t>(streams[k]) : nullptr;
+        rc = decode_device(d_bits[k], nwords[k], lens[k], d_out[k], s);
+        if (rc != CN_OK) return rc;
+    }
+    return CN_OK;
+}
+
+int enable_peer_access(const int *devices, int count)
+{
+    if (count < 1 || !devices) return fail(CN_ERR_ARG, "cn_enable_peer_access: bad arguments");
+    DeviceGuard guard;
+    for (int i = 0; i < count; i++) {
+        CN_CUDA(cudaSetDevice(devices[i]));
+        for (int j = 0; j < count; j++) {
+            if (i == j) continue;
+            int can = 0;
+            CN_CUDA(cudaDeviceCanAccessPeer(&can, devices[i], devices[j]));
+            if (!can) return fail(CN_ERR_CUDA, "cn_enable_peer_access: device %d cannot access device %d", devices[i], devices[j]);
+            cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); continue; }
+            if (e != cudaSuccess) return fail(CN_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", devices[i], devices[j], cudaGetErrorString(e));
+        }
+    }
+    return CN_OK;
+}
+
+int synchronize_devices(const int *devices, int count)
+{
+    if (count < 1 || !devices) return fail(CN_ERR_ARG, "cn_synchronize_devices: bad arguments");
+    DeviceGuard guard;
+    for (int i = 0; i < count; i++) {
+        CN_CUDA(cudaSetDevice(devices[i]));
+        CN_CUDA(cudaDeviceSynchronize());
+    }
+    return CN_OK;
+}
+
+}  // namespace

@@ -21,8 +21,12 @@ from ._lib import LengthError, check
 
 __all__ = [
     "n_to_bits_cuda", "bits_to_n_cuda", "words_for_len", "n_to_bits_checked_cuda", "encode_checked_device",
+    "n_to_bits_lut_cuda", "n_to_bits_ex_cuda", "encode_ex_device",
     "encode_device", "decode_device", "generate_device", "generate_words_device", "LengthError",
+    "ENC_PLAIN", "ENC_COUNT", "ENC_LUT_EXACT",
 ]
+
+ENC_PLAIN, ENC_COUNT, ENC_LUT_EXACT = _lib.CN_ENC_PLAIN, _lib.CN_ENC_COUNT, _lib.CN_ENC_LUT_EXACT
 
 
 def words_for_len(length: int) -> int:
@@ -55,6 +59,22 @@ def n_to_bits_checked_cuda(n):
     invalid = ctypes.c_uint64(0)
     check(_lib.load().cn_n_to_bits_checked_host(src.ctypes.data, src.size, out.ctypes.data, ctypes.byref(invalid)))
     return out, int(invalid.value)
+
+
+def n_to_bits_ex_cuda(n, mode: int):
+    """Encode with an explicit treatment of bytes outside {A,C,G,T,U,a,c,g,t,u} (include/cute_nucleotides_cuda.h):
+    ENC_PLAIN -> (byte >> 1) & 3 like the reference's SIMD encoders; ENC_COUNT -> same words + count;
+    ENC_LUT_EXACT -> code 0 like n_to_bits_lut's BYTE_LUT (src/n_to_bits.rs:8-21).  Returns (words, invalid_count)."""
+    src = _as_u8(n)
+    out = np.empty(words_for_len(src.size), dtype=np.uint64)
+    invalid = ctypes.c_uint64(0)
+    check(_lib.load().cn_n_to_bits_ex_host(src.ctypes.data, src.size, out.ctypes.data, mode, ctypes.byref(invalid)))
+    return out, int(invalid.value)
+
+
+def n_to_bits_lut_cuda(n) -> np.ndarray:
+    """Bit-exact n_to_bits_lut (src/n_to_bits.rs:34-47) on EVERY input, including bytes outside the alphabet (-> 0)."""
+    return n_to_bits_ex_cuda(n, ENC_LUT_EXACT)[0]
 
 
 def bits_to_n_cuda(bits, length: int) -> bytes:
@@ -105,6 +125,23 @@ def encode_checked_device(n, counter, out=None, stream=None):
         out = torch.empty(words_for_len(length), dtype=torch.int64, device=n.device)
     with torch.cuda.device(n.device):
         check(_lib.load().cn_encode_checked_device(n.data_ptr(), length, out.data_ptr(), counter.data_ptr(), _stream_ptr(stream)))
+    return out
+
+
+def encode_ex_device(n, mode: int, counter=None, out=None, stream=None):
+    """encode_device with an explicit mode (ENC_PLAIN / ENC_COUNT / ENC_LUT_EXACT); `counter` (one-element int64 CUDA
+    tensor, incremented) is required for ENC_COUNT and optional for ENC_LUT_EXACT."""
+    import torch
+    if n.dtype != torch.uint8 or not n.is_cuda or not n.is_contiguous():
+        raise TypeError("encode_ex_device expects a contiguous uint8 CUDA tensor")
+    if counter is not None and (counter.element_size() != 8 or counter.numel() < 1 or not counter.is_cuda):
+        raise TypeError("counter must be a one-element 8-byte CUDA tensor")
+    length = n.numel()
+    if out is None:
+        out = torch.empty(words_for_len(length), dtype=torch.int64, device=n.device)
+    with torch.cuda.device(n.device):
+        check(_lib.load().cn_encode_ex_device(n.data_ptr(), length, out.data_ptr(), mode,
+                                              counter.data_ptr() if counter is not None else None, _stream_ptr(stream)))
     return out
 
 

@@ -8,13 +8,16 @@ Same conventions as n_to_bits.py: every call goes through the C ABI, no CPU path
 reference panics (:79-81)."""
 from __future__ import annotations
 
+import ctypes
+
 import numpy as np
 
 from . import _lib
 from ._lib import LengthError, check
 from .n_to_bits import _as_u8, _stream_ptr
 
-__all__ = ["n_to_bits2_cuda", "bits_to_n2_cuda", "words2_for_len", "encode2_device", "decode2_device", "generate2_device"]
+__all__ = ["n_to_bits2_cuda", "bits_to_n2_cuda", "words2_for_len", "encode2_device", "decode2_device", "generate2_device",
+           "n_to_bits2_ex_cuda", "n_to_bits2_lut_cuda", "encode2_ex_device"]
 
 
 def words2_for_len(length: int) -> int:
@@ -28,6 +31,22 @@ def n_to_bits2_cuda(n) -> np.ndarray:
     if src.size:
         check(_lib.load().cn_n_to_bits2_host(src.ctypes.data, src.size, out.ctypes.data))
     return out
+
+
+def n_to_bits2_ex_cuda(n, mode: int):
+    """Base-5 encode with an explicit treatment of bytes outside {A,C,G,T,U,N,a,c,g,t,u,n}: ENC_PLAIN -> digit looked up by
+    the low 3 bits like n_to_bits2_pext (src/n_to_bits2.rs:127-136); ENC_COUNT -> same words + count; ENC_LUT_EXACT ->
+    digit 0 like n_to_bits2_lut's BYTE_LUT (:8-23).  Returns (words, invalid_count)."""
+    src = _as_u8(n)
+    out = np.empty(words2_for_len(src.size), dtype=np.uint64)
+    invalid = ctypes.c_uint64(0)
+    check(_lib.load().cn_n_to_bits2_ex_host(src.ctypes.data, src.size, out.ctypes.data, mode, ctypes.byref(invalid)))
+    return out, int(invalid.value)
+
+
+def n_to_bits2_lut_cuda(n) -> np.ndarray:
+    """Bit-exact n_to_bits2_lut (src/n_to_bits2.rs:37-74) on every input."""
+    return n_to_bits2_ex_cuda(n, _lib.CN_ENC_LUT_EXACT)[0]
 
 
 def bits_to_n2_cuda(bits, length: int) -> bytes:
@@ -50,6 +69,19 @@ def encode2_device(n, out=None, stream=None):
         raise ValueError("out must be a contiguous 8-byte-element tensor with ceil(len/27) elements")
     with torch.cuda.device(n.device):
         check(_lib.load().cn_encode2_device(n.data_ptr(), length, out.data_ptr(), _stream_ptr(stream)))
+    return out
+
+
+def encode2_ex_device(n, mode: int, counter=None, out=None, stream=None):
+    import torch
+    if n.dtype != torch.uint8 or not n.is_cuda or not n.is_contiguous():
+        raise TypeError("encode2_ex_device expects a contiguous uint8 CUDA tensor")
+    length = n.numel()
+    if out is None:
+        out = torch.empty(words2_for_len(length), dtype=torch.int64, device=n.device)
+    with torch.cuda.device(n.device):
+        check(_lib.load().cn_encode2_ex_device(n.data_ptr(), length, out.data_ptr(), mode,
+                                               counter.data_ptr() if counter is not None else None, _stream_ptr(stream)))
     return out
 
 

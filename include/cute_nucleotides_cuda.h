@@ -1,7 +1,7 @@
 /*
  * cute_nucleotides_cuda.h -- C ABI of the B200 (sm_100a) implementation of cute-nucleotides' 2-bit
  * nucleotide codec.  This is the drop-in boundary: the entry points are exactly what a Rust `extern "C"`
- * block (rust/src/ffi.rs) binds to put `n_to_bits_cuda` / `bits_to_n_cuda` next
+ * block (`mod ffi` in rust/src/lib.rs) binds to put `n_to_bits_cuda` / `bits_to_n_cuda` next
  * to the reference's `n_to_bits_{lut,pext,shift,movemask,mul}` / `bits_to_n_{lut,shuffle,pdep,clmul}`.
  *
  * Reference interface replaced (paths relative to the reference repo):
@@ -15,9 +15,10 @@
  *   - codes: A/a = 0, C/c = 1, T/t/U/u = 2, G/g = 3 (case-insensitive)
  *   - ceil(len/32) words are produced; unused high bits of the last word are zero
  *   - decoding always yields upper-case 'A','C','T','G'
- *   - bytes outside {A,C,G,T,U,a,c,g,t,u} are mapped by (byte >> 1) & 3 like the reference's SIMD
- *     encoders (pext/shift/movemask/mul); the reference's variants disagree with each other on such
- *     bytes, so parity is defined on the valid alphabet only.
+ *   - bytes outside {A,C,G,T,U,a,c,g,t,u}: the reference's variants disagree with each other.  The plain entry
+ *     points map them by (byte >> 1) & 3 like its SIMD encoders (pext/shift/movemask/mul); mode
+ *     CN_ENC_LUT_EXACT of the *_ex_* entry points maps them to 0 exactly like n_to_bits_lut's BYTE_LUT
+ *     (src/n_to_bits.rs:8-21, :42), so either behaviour of the reference is reproducible bit for bit.
  *
  * Conventions: every function returns CN_OK (0) or a CN_ERR_* code and never throws or aborts;
  * cn_last_error() returns a thread-local description of the last failure on the calling thread.
@@ -26,7 +27,9 @@
  * All entry points are thread-safe; the host-slice calls keep per-thread staging state (released when the thread
  * exits).  Input and output buffers of one call must not overlap (the reference's functions cannot alias either: they
  * return a fresh Vec); decoding back over the buffer that was ENCODED earlier is fine (separate calls).
- * The cn_set_* knobs are process-wide harness switches: set them before issuing calls, not concurrently with them.
+ * The cn_set_* knobs are process-wide; each is a single atomic word, so a call racing with a setter sees the old or
+ * the new value, never a mix (a call snapshots its knobs once).
+ * No entry point reads memory outside the buffers it is given (unaligned buffers included).
  */
 #ifndef CUTE_NUCLEOTIDES_CUDA_H
 #define CUTE_NUCLEOTIDES_CUDA_H
@@ -44,7 +47,7 @@ extern "C" {
 #define CN_ERR_ARG     3   /* null / misaligned pointer or bad enum */
 #define CN_ERR_NOMEM   4   /* staging allocation failed */
 
-#define CN_ABI_VERSION 1
+#define CN_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define CN_API __attribute__((visibility("default")))
@@ -100,6 +103,59 @@ CN_API int cn_ipc_close(void *d_ptr, size_t offset);
 CN_API int cn_n_to_bits_checked_host(const uint8_t *n, size_t len, uint64_t *out, uint64_t *invalid_count);
 CN_API int cn_encode_checked_device(const void *d_n, size_t len, void *d_out, void *d_invalid_count, void *stream);
 
+/* ---- encode with a choice of semantics for bytes outside the alphabet --------------------------------------- */
+#define CN_ENC_PLAIN      0   /* (byte >> 1) & 3 for every byte: n_to_bits_{pext,shift,movemask,mul} (src/n_to_bits.rs:85,100) */
+#define CN_ENC_COUNT      1   /* same words as PLAIN + count of the bytes outside the alphabet (= the *_checked_* entry points) */
+#define CN_ENC_LUT_EXACT  2   /* bytes outside the alphabet (and bytes >= 0x80, an out-of-bounds LUT read in the reference)
+                                 encode as 0: bit-exact n_to_bits_lut (BYTE_LUT, src/n_to_bits.rs:8-21, :42) on ALL inputs;
+                                 the offending bytes are counted too when a counter is given */
+/* invalid_count may be NULL except in mode CN_ENC_COUNT.  Device flavour: *d_invalid_count is INCREMENTED. */
+CN_API int cn_n_to_bits_ex_host(const uint8_t *n, size_t len, uint64_t *out, int mode, uint64_t *invalid_count);
+CN_API int cn_encode_ex_device(const void *d_n, size_t len, void *d_out, int mode, void *d_invalid_count, void *stream);
+/* The same three modes for the base-5 codec; its alphabet is {A,C,G,T,U,N,a,c,g,t,u,n}.  PLAIN looks digits up by the low
+ * 3 bits like n_to_bits2_pext's pshufb LUT (src/n_to_bits2.rs:127-136); LUT_EXACT maps everything unlisted to digit 0 like
+ * n_to_bits2_lut's BYTE_LUT (src/n_to_bits2.rs:8-23). */
+CN_API int cn_n_to_bits2_ex_host(const uint8_t *n, size_t len, uint64_t *out, int mode, uint64_t *invalid_count);
+CN_API int cn_encode2_ex_device(const void *d_n, size_t len, void *d_out, int mode, void *d_invalid_count, void *stream);
+
+/* ---- multi-GPU inside ONE process (SURVEY 8b cn_encode_sharded, 8e) ------------------------------------------ */
+/* Devices the HOST-SLICE calls fan out over.  With count >= 2, one cn_n_to_bits_host / cn_bits_to_n_host (and _ex_, base-5)
+ * call is cut by sequence offset into word-aligned ranges (word w depends only on nucleotides 32w..32w+31,
+ * src/n_to_bits.rs:39-42) and every range runs on its own GPU -- count PCIe links instead of one -- driven by a worker
+ * thread per device inside the library; the result is identical.  count == 0 restores the single-device behaviour
+ * (the device chosen with cn_init, else the current one).  Environment: CN_DEVICES=all or CN_DEVICES=0,1,2 does the same
+ * for an unmodified caller. */
+CN_API int cn_set_devices(const int *devices, int count);
+CN_API int cn_get_devices(int *devices, int capacity, int *count);
+/* The shard planner: range [*start, *end) of shard `shard` of `nshards` over total_len nucleotides; boundaries are
+ * multiples of `granule` (a multiple of 32 for the 2-bit codec, of 27 for base-5), the ragged tail goes to the last shard. */
+CN_API int cn_shard_bounds(size_t total_len, int nshards, int shard, size_t granule, size_t *start, size_t *end);
+/* Device-resident shards, one per device, launched from the calling thread (asynchronous; streams may be NULL = every
+ * device's default stream, else streams[k] is a cudaStream_t of devices[k]).  Shard k: lens[k] nucleotides at d_n[k] ->
+ * cn_words_for_len(lens[k]) words at d_out[k].  After cn_enable_peer_access a d_out[k] (encode) or d_bits[k] (decode) may
+ * point into ANOTHER device's memory: the stores / loads then cross NVLink inside the kernel, i.e. encode + gather-to-root
+ * and scatter + decode are single kernels with no separate collective. */
+CN_API int cn_encode_sharded(int nshards, const int *devices, const void *const *d_n, const size_t *lens,
+                             void *const *d_out, void *const *streams);
+CN_API int cn_decode_sharded(int nshards, const int *devices, const void *const *d_bits, const size_t *nwords,
+                             const size_t *lens, void *const *d_out, void *const *streams);
+CN_API int cn_enable_peer_access(const int *devices, int count);
+CN_API int cn_synchronize_devices(const int *devices, int count);
+
+/* ---- operations on packed 2-bit words ---------------------------------------------------------- */
+/* PARITY UNPINNED: the reference motivates these (README.md:21-23, 45, 415-418) but holds no code for them.  They are
+ * defined through the reference's own codec: hamming = number of i < len with bits_to_n_lut(a)[i] != bits_to_n_lut(b)[i];
+ * complement = n_to_bits_lut of the decoded sequence with A<->T, C<->G; reverse_complement = the same, reversed.  Only the
+ * first len nucleotides (ceil(len/32) words) are read; unused high bits of the last output word are zero;
+ * CN_ERR_LENGTH when len > 32 * nwords.  Words 8-byte aligned (32-byte aligned takes the fast path).
+ * *d_result (device uint64) is INCREMENTED: zero it first.  reverse_complement cannot run in place. */
+CN_API int cn_hamming_device(const void *d_a, const void *d_b, size_t nwords, size_t len, void *d_result, void *stream);
+CN_API int cn_complement_device(const void *d_bits, size_t nwords, size_t len, void *d_out, void *stream);
+CN_API int cn_reverse_complement_device(const void *d_bits, size_t nwords, size_t len, void *d_out, void *stream);
+CN_API int cn_hamming_host(const uint64_t *a, const uint64_t *b, size_t nwords, size_t len, uint64_t *result);
+CN_API int cn_complement_host(const uint64_t *bits, size_t nwords, size_t len, uint64_t *out);
+CN_API int cn_reverse_complement_host(const uint64_t *bits, size_t nwords, size_t len, uint64_t *out);
+
 /* ---- base-5 codec: {A,C,T/U,G,N} -> digits 0..4, 3 digits -> 7 bits, 27 nucleotides per u64 ------------ */
 /* (len / 27) + (len % 27 != 0): words produced by n_to_bits2_* (src/n_to_bits2.rs:38, :121). */
 CN_API size_t cn_words2_for_len(size_t len);
@@ -143,6 +199,12 @@ CN_API int cn_get_tuning(int direction, int *vec, int *unroll, int *threads);
  * 1 = zero-copy (kernel reads/writes pinned host memory directly over PCIe).  chunk_bytes = ASCII bytes
  * per pipeline chunk (0 keeps the current value). */
 CN_API int cn_set_host_strategy(int strategy, size_t chunk_bytes);
+/* Chunk sizes of the staged pipeline (0 keeps a value): pinned caller buffers are DMA'd in pinned_chunk pieces, pageable
+ * ones staged in pageable_chunk pieces.  cn_set_host_strategy's chunk_bytes sets both. */
+CN_API int cn_set_host_chunks(size_t pinned_chunk, size_t pageable_chunk);
+/* Threads that copy pageable caller memory to / from pinned staging (the waiting caller included).  0 = default:
+ * CN_HOST_THREADS, else min(8, cores/2).  The pool only grows; a lower value takes effect for new pools only. */
+CN_API int cn_set_host_threads(int threads);
 
 #ifdef __cplusplus
 }

@@ -412,6 +412,53 @@ static void init_tables2(void)
     g_byte_lut2['n'] = 4; g_byte_lut2['N'] = 4;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Operations on packed words.  PARITY UNPINNED: the reference holds no code for   */
+/* them (README.md:21-23, 45, 415-418 only motivate them), so they are DEFINED through the        */
+/* reference's own codec, via ASCII: decode with bits_to_n_lut, operate on letters, re-encode     */
+/* with n_to_bits_lut.  Returns 1 where bits_to_n_lut would panic.                                */
+/* ------------------------------------------------------------------------------------------ */
+CN_EXPORT int oracle_hamming(const uint64_t *a, const uint64_t *b, size_t nwords, size_t len, uint64_t *result)
+{
+    uint8_t *x = malloc(len ? len : 1), *y = malloc(len ? len : 1);
+    int rc = oracle_bits_to_n_lut(a, nwords, len, x);
+    if (rc == 0) rc = oracle_bits_to_n_lut(b, nwords, len, y);
+    uint64_t d = 0;
+    if (rc == 0) for (size_t i = 0; i < len; i++) d += x[i] != y[i];
+    *result = d;
+    free(x); free(y);
+    return rc;
+}
+
+CN_EXPORT int oracle_complement(const uint64_t *bits, size_t nwords, size_t len, uint64_t *out, int reverse)
+{
+    uint8_t *x = malloc(len ? len : 1), *y = malloc(len ? len : 1);
+    int rc = oracle_bits_to_n_lut(bits, nwords, len, x);
+    if (rc == 0) {
+        for (size_t i = 0; i < len; i++) {
+            uint8_t c = x[i];
+            c = c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'C' ? 'G' : 'C';
+            y[reverse ? len - 1 - i : i] = c;
+        }
+        oracle_n_to_bits_lut(y, len, out);
+    }
+    free(x); free(y);
+    return rc;
+}
+
+CN_EXPORT size_t oracle_count_invalid2(const uint8_t *n, size_t len)
+{   /* bytes outside {ACGTUNacgtun}: n_to_bits2_lut maps them to digit 0 (:8-23), n_to_bits2_pext by their low 3 bits (:127-136) */
+    size_t bad = 0;
+    for (size_t i = 0; i < len; i++) {
+        switch (n[i]) {
+        case 'A': case 'C': case 'G': case 'T': case 'U': case 'N':
+        case 'a': case 'c': case 'g': case 't': case 'u': case 'n': break;
+        default: bad++;
+        }
+    }
+    return bad;
+}
+
 CN_EXPORT size_t oracle_words2_for_len(size_t len)
 {   /* src/n_to_bits2.rs:38 */
     return len / 27 + ((len % 27) ? 1 : 0);

@@ -45,6 +45,10 @@ class Oracle:
         L.oracle_generate_mt.restype, L.oracle_generate_mt.argtypes = c_int, [c_void_p, c_size_t, c_size_t, c_uint64, c_int, c_int]
         L.oracle_generate_words.restype, L.oracle_generate_words.argtypes = None, [c_void_p, c_size_t, c_size_t, c_uint64]
         L.oracle_canonical.restype, L.oracle_canonical.argtypes = None, [c_void_p, c_size_t, c_void_p]
+        L.oracle_count_invalid2.restype = c_size_t
+        L.oracle_count_invalid2.argtypes = [c_void_p, c_size_t]
+        L.oracle_hamming.restype, L.oracle_hamming.argtypes = c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]
+        L.oracle_complement.restype, L.oracle_complement.argtypes = c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_int]
         L.oracle_cpu_ok.restype = c_int
         L.oracle_words2_for_len.restype, L.oracle_words2_for_len.argtypes = c_size_t, [c_size_t]
         for v in ENCODERS2:
@@ -126,6 +130,28 @@ class Oracle:
     def count_invalid(self, n) -> int:
         a = self._u8(n)
         return self.lib.oracle_count_invalid(a.ctypes.data, a.size)
+
+    # -- operations on packed words, defined through the codec (parity unpinned: no reference code) -------
+    def hamming(self, a, b, length: int) -> int:
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        b = np.ascontiguousarray(b, dtype=np.uint64)
+        res = ctypes.c_uint64(0)
+        rc = self.lib.oracle_hamming(a.ctypes.data, b.ctypes.data, min(a.size, b.size), length, ctypes.byref(res))
+        if rc == 1:
+            raise ValueError("The length is greater than the number of nucleotides!")
+        return int(res.value)
+
+    def complement(self, bits, length: int, reverse: bool = False) -> np.ndarray:
+        w = np.ascontiguousarray(bits, dtype=np.uint64)
+        out = np.empty(self.words_for_len(length), dtype=np.uint64)
+        rc = self.lib.oracle_complement(w.ctypes.data, w.size, length, out.ctypes.data, int(reverse))
+        if rc == 1:
+            raise ValueError("The length is greater than the number of nucleotides!")
+        return out
+
+    def count_invalid2(self, n) -> int:
+        a = self._u8(n)
+        return self.lib.oracle_count_invalid2(a.ctypes.data, a.size)
 
     # -- base-5 codec (src/n_to_bits2.rs) --------------------------------------------------------------
     def words2_for_len(self, length: int) -> int:

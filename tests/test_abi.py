@@ -45,6 +45,29 @@ def test_pure_host_entry_points(cn):
     assert lib.cn_set_tuning(0, 24, 4, 256) == _lib.CN_ERR_ARG and b"unsupported" in lib.cn_last_error()
 
 
+def test_shard_planner_matches_python(cn):
+    """cn_shard_bounds (what a Rust / C++ caller plans with) == sharded.shard_bounds (what the torch.distributed path uses)."""
+    from cute_nucleotides_b200 import sharded
+    for total in (0, 1, 31, 32, 33, 100003, (1 << 26) + 77, 10 * (1 << 30) + 21):
+        for world in (1, 2, 3, 8):
+            for granule in (32, 1 << 20):
+                for r in range(world):
+                    assert cn.shard_bounds_c(total, world, r, granule) == sharded.shard_bounds(total, world, r, granule)
+    for total, world, granule in ((10 ** 6, 4, 27 * 128), (27 * 5 + 3, 3, 27)):
+        for r in range(world):
+            assert cn.shard_bounds_c(total, world, r, granule) == sharded.shard_bounds(total, world, r, granule, group=27)
+
+
+def test_host_knobs_validate_their_arguments(cn):
+    from cute_nucleotides_b200 import _lib
+    lib = _lib.load()
+    assert lib.cn_set_host_threads(-1) == _lib.CN_ERR_ARG and lib.cn_set_host_threads(65) == _lib.CN_ERR_ARG
+    assert lib.cn_set_host_threads(0) == 0
+    assert lib.cn_set_host_chunks(1000, 0) == _lib.CN_ERR_ARG and lib.cn_set_host_chunks(0, 4097) == _lib.CN_ERR_ARG
+    assert lib.cn_set_host_chunks(0, 0) == 0 and lib.cn_set_host_chunks(16 << 20, 4 << 20) == 0
+    assert cn.get_devices() == []                     # no device set unless cn_set_devices / CN_DEVICES says so
+
+
 def test_length_check_needs_no_gpu(cn):
     # len > 32*nwords is rejected before any CUDA call, with the reference's panic text (src/n_to_bits.rs:52-54)
     with pytest.raises(cn.LengthError, match="The length is greater than the number of nucleotides!"):

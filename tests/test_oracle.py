@@ -178,3 +178,28 @@ def test_property_roundtrip_and_shard_linearity(oracle):
                 assert oracle.bits_to_n(words, len(n), v) == oracle.canonical(n)
 
     check()
+
+
+# ---------------------------------------------------------------------------------------------------
+# operations on packed words -- PARITY UNPINNED (no reference code): the oracle defines them through
+# ASCII with the reference's codec; here that definition is cross-checked against the bit-level formulation
+# (complement = code ^ 2, mismatch = non-zero 2-bit field of a ^ b) in numpy.
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("size", [0, 1, 31, 32, 33, 64, 1000, 4097])
+def test_packed_ops_definition_vs_bit_formulation(oracle, size):
+    n = oracle.generate(size, seed=size + 1, alphabet=10)
+    m = oracle.generate(size, seed=size + 2, alphabet=10)
+    a, b = oracle.n_to_bits(n, "lut"), oracle.n_to_bits(m, "lut")
+    x = a ^ b
+    fields = (x | (x >> np.uint64(1))) & np.uint64(0x5555555555555555)
+    assert oracle.hamming(a, b, size) == sum(bin(int(f)).count("1") for f in fields)
+    valid = np.full(a.size, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
+    if size % 32:
+        valid[-1] = np.uint64((1 << (2 * (size % 32))) - 1)
+    assert np.array_equal(oracle.complement(a, size), (a ^ np.uint64(0xAAAAAAAAAAAAAAAA)) & valid)
+    codes = np.array([(int(a[i >> 5]) >> (2 * (i & 31))) & 3 for i in range(size)], dtype=np.uint64)
+    rc_codes = (codes ^ np.uint64(2))[::-1]
+    expect = np.zeros(a.size, dtype=np.uint64)
+    for i, c in enumerate(rc_codes):
+        expect[i >> 5] |= np.uint64(int(c) << (2 * (i & 31)))
+    assert np.array_equal(oracle.complement(a, size, reverse=True), expect)

@@ -342,6 +342,23 @@ def test_host_api_is_thread_safe(cn, oracle):
     assert not errors, errors
 
 
+def test_pageable_host_slices_above_4gib(cn, oracle):
+    """The literal drop-in shape at scale: pageable (numpy / Vec-like) buffers on both sides, > 2^32 nucleotides, so the
+    staged pipeline's 64-bit offsets, the copier pool and thousands of ring wrap-arounds are all on the path."""
+    size = (1 << 32) + (1 << 20) + 21
+    n = oracle.generate(size, seed=0xABCD, alphabet=10)
+    got = cn.n_to_bits_cuda(n)
+    ref = oracle.encode_mt(n, "lut")
+    assert np.array_equal(got, ref)
+    del ref
+    out = np.frombuffer(cn.bits_to_n_cuda(got, size), dtype=np.uint8)
+    lut = np.zeros(256, dtype=np.uint8)
+    for ch, canon in zip(b"ACGTUacgtu", b"ACGTTACGTT"):
+        lut[ch] = canon
+    for s in range(0, size, 1 << 28):
+        assert np.array_equal(out[s:s + (1 << 28)], lut[n[s:s + (1 << 28)]]), s
+
+
 # ---------------------------------------------------------------------------------------------------
 # encode + validation in one pass (SURVEY 8f-3)
 # ---------------------------------------------------------------------------------------------------

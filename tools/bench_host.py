@@ -1,5 +1,7 @@
-"""Sweep the host-slice pipeline (strategy x chunk size) on pinned and pageable buffers; prints JSON lines.
-Usage (GPU box): python tools/bench_host.py [GiB]"""
+"""Sweep the host-slice pipeline on pinned and pageable buffers; prints JSON lines.
+Usage (GPU box): python tools/bench_host.py [GiB] [pinned|pageable|all]
+pinned:   strategy x chunk size
+pageable: copier threads (ascending: the pool only grows) x staging chunk size"""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -9,6 +11,7 @@ import cute_nucleotides_b200 as cn
 from cute_nucleotides_b200 import _lib
 lib = _lib.load()
 gib = float(sys.argv[1]) if len(sys.argv) > 1 else 4
+what = sys.argv[2] if len(sys.argv) > 2 else "all"
 L = int(gib * (1 << 30))
 W = cn.words_for_len(L)
 tmp = cn.generate_device(torch.empty(L, dtype=torch.uint8, device="cuda"), 0, 3, 10)
@@ -29,14 +32,24 @@ def run(name, enc, dec, reps=3):
     return {"case": name, "encode_gnt_s": round(L / te / 1e9, 2), "decode_gnt_s": round(L / td / 1e9, 2),
             "roundtrip_gnt_s": round(L / (te + td) / 1e9, 2)}
 
-for strategy in (0, 1):
-    for chunk_mib in (4, 16, 64, 256):
-        _lib.check(lib.cn_set_host_strategy(strategy, chunk_mib << 20))
-        r = run("pinned", lambda: _lib.check(lib.cn_n_to_bits_host(pin_n.data_ptr(), L, pin_bits.data_ptr())),
-                lambda: _lib.check(lib.cn_bits_to_n_host(pin_bits.data_ptr(), W, L, pin_out.data_ptr())))
-        r.update(strategy=strategy, chunk_mib=chunk_mib); print(json.dumps(r), flush=True)
-for chunk_mib in (4, 16, 64):
-    _lib.check(lib.cn_set_host_strategy(0, chunk_mib << 20))
-    r = run("pageable (pre-faulted)", lambda: _lib.check(lib.cn_n_to_bits_host(pg_n.ctypes.data, L, pg_bits.ctypes.data)),
-            lambda: _lib.check(lib.cn_bits_to_n_host(pg_bits.ctypes.data, W, L, pg_out.ctypes.data)))
-    r.update(strategy=0, chunk_mib=chunk_mib); print(json.dumps(r), flush=True)
+if what in ("all", "pinned"):
+    for strategy in (0, 1):
+        for chunk_mib in (4, 16, 64):
+            _lib.check(lib.cn_set_host_strategy(strategy, chunk_mib << 20))
+            r = run("pinned", lambda: _lib.check(lib.cn_n_to_bits_host(pin_n.data_ptr(), L, pin_bits.data_ptr())),
+                    lambda: _lib.check(lib.cn_bits_to_n_host(pin_bits.data_ptr(), W, L, pin_out.data_ptr())))
+            r.update(strategy=strategy, chunk_mib=chunk_mib); print(json.dumps(r), flush=True)
+    _lib.check(lib.cn_set_host_strategy(0, 16 << 20))
+if what in ("all", "pageable"):
+    ok = None
+    for threads in (2, 4, 6, 8, 10, 12, 16):
+        if threads > (os.cpu_count() or 1):
+            break
+        _lib.check(lib.cn_set_host_threads(threads))
+        for chunk_kib in (512, 1024, 2048, 4096, 8192, 16384):
+            _lib.check(lib.cn_set_host_chunks(0, chunk_kib << 10))
+            r = run("pageable (pre-faulted)", lambda: _lib.check(lib.cn_n_to_bits_host(pg_n.ctypes.data, L, pg_bits.ctypes.data)),
+                    lambda: _lib.check(lib.cn_bits_to_n_host(pg_bits.ctypes.data, W, L, pg_out.ctypes.data)), reps=2)
+            if ok is None:
+                ok = bool(np.array_equal(pg_bits.view(np.int64), pin_bits.numpy())) if what == "all" else True
+            r.update(threads=threads, chunk_kib=chunk_kib, verified=ok); print(json.dumps(r), flush=True)
