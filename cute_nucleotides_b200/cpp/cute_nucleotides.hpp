@@ -55,6 +55,37 @@ inline Words n_to_bits_cuda(std::string_view n)
 }
 inline Words n_to_bits_cuda(const std::vector<uint8_t> &n) { return n_to_bits_cuda(n.data(), n.size()); }
 
+/// n_to_bits_lut-exact: bytes outside {A,C,G,T,U,a,c,g,t,u} encode as 0 like BYTE_LUT (src/n_to_bits.rs:8-21), so the result
+/// equals n_to_bits_lut(n) on EVERY input; *invalid (optional) receives the number of such bytes.
+inline Words n_to_bits_lut_cuda(const uint8_t *n, size_t len, uint64_t *invalid = nullptr)
+{
+    Words res(cn_words_for_len(len));
+    uint64_t count = 0;
+    check_status(cn_n_to_bits_ex_host(n, len, res.data(), CN_ENC_LUT_EXACT, &count));
+    if (invalid) *invalid = count;
+    return res;
+}
+
+/// Many independent sequences in ONE call (one kernel launch for thousands of reads): element i == n_to_bits_cuda(seqs[i]).
+inline std::vector<Words> n_to_bits_cuda_batch(const std::vector<std::string_view> &seqs)
+{
+    std::vector<Words> res(seqs.size());
+    std::vector<const uint8_t *> in(seqs.size());
+    std::vector<size_t> lens(seqs.size());
+    std::vector<uint64_t *> out(seqs.size());
+    for (size_t i = 0; i < seqs.size(); i++) {
+        in[i] = reinterpret_cast<const uint8_t *>(seqs[i].data());
+        lens[i] = seqs[i].size();
+        res[i] = Words(cn_words_for_len(lens[i]));
+        out[i] = res[i].data();
+    }
+    check_status(cn_n_to_bits_host_batch(in.data(), lens.data(), seqs.size(), out.data()));
+    return res;
+}
+
+/// Fan every later *_cuda call out over these GPUs (one PCIe link each); an empty list restores single-GPU behaviour.
+inline void set_devices(const std::vector<int> &devices) { check_status(cn_set_devices(devices.data(), (int)devices.size())); }
+
 /// Decode pairs of bits from packed 64-bit integers to a byte string of `{A, T, C, G}` on the GPU.
 /// Mirrors bits_to_n_lut (src/n_to_bits.rs:51): throws std::length_error if len > 32 * bits.size().
 inline Bytes bits_to_n_cuda(const uint64_t *bits, size_t nwords, size_t len)

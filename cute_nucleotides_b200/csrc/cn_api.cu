@@ -88,6 +88,20 @@ int cn_bits_to_n_host(const uint64_t *bits, size_t nwords, size_t len, uint8_t *
     return host_codec(kCodec2bit, false, reinterpret_cast<const uint8_t *>(bits), out, len);
 }
 
+int cn_n_to_bits_host_batch(const uint8_t *const *seqs, const size_t *lens, size_t count, uint64_t *const *outs)
+{
+    if (count == 0) return CN_OK;
+    if (!seqs || !lens || !outs) return fail(CN_ERR_ARG, "cn_n_to_bits_host_batch: null pointer");
+    return host_batch_one(true, reinterpret_cast<const void *const *>(seqs), lens, count, reinterpret_cast<void *const *>(outs));
+}
+
+int cn_bits_to_n_host_batch(const uint64_t *const *bits, const size_t *lens, size_t count, uint8_t *const *outs)
+{
+    if (count == 0) return CN_OK;
+    if (!bits || !lens || !outs) return fail(CN_ERR_ARG, "cn_bits_to_n_host_batch: null pointer");
+    return host_batch_one(false, reinterpret_cast<const void *const *>(bits), lens, count, reinterpret_cast<void *const *>(outs));
+}
+
 int cn_n_to_bits_checked_host(const uint8_t *n, size_t len, uint64_t *out, uint64_t *invalid_count)
 {
     if (!invalid_count) return fail(CN_ERR_ARG, "cn_n_to_bits_checked_host: null counter");

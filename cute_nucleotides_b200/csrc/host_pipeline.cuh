@@ -23,9 +23,12 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// Copy flavours of the staging copier.  CN_HOST_COPY=nt selects non-temporal (streaming) stores: the destination is
-// written around the cache, which saves the read-for-ownership of every destination line.  Default: glibc memcpy,
-// which measured faster on the boxes profiled (tools/host_ceiling: 151 vs 121 GB/s of traffic on 8 threads).
+// Copy flavours of the staging copier: glibc memcpy, or AVX2 non-temporal (streaming) stores that write the destination
+// around the cache.  Measured inside the pipeline on a 16-vCPU B200 box (profiles/host_r02_pageable_sweep.jsonl, 4 GiB,
+// 10 copiers, 4 MiB chunks): copying INTO pinned staging is as fast or faster with memcpy (48 vs 44 Gnt/s encode: the
+// chunk is still in the last-level cache when the DMA engine reads it), copying OUT of staging into the caller's
+// buffer -- which nobody reads again soon -- is faster with streaming stores (39 vs 34 Gnt/s decode).  Those are the
+// defaults; CN_HOST_COPY_IN / CN_HOST_COPY_OUT = memcpy | nt override them for A/B runs.
 // ------------------------------------------------------------------------------------------------
 __attribute__((target("avx2"))) inline void copy_nt_avx2(uint8_t *dst, const uint8_t *src, size_t bytes)
 {
@@ -47,19 +50,27 @@ __attribute__((target("avx2"))) inline void copy_nt_avx2(uint8_t *dst, const uin
     _mm_sfence();
     memcpy(dst + body, src + body, bytes - body);
 }
-const bool g_copy_nt = [] {
-    const char *env = std::getenv("CN_HOST_COPY");
-    return env && !strcmp(env, "nt") && __builtin_cpu_supports("avx2");
-}();
-inline void staging_copy(uint8_t *dst, const uint8_t *src, size_t bytes)
+inline bool copy_flavour_nt(const char *name, bool dflt)
 {
-    if (g_copy_nt) copy_nt_avx2(dst, src, bytes);
+    if (!__builtin_cpu_supports("avx2")) return false;
+    const char *env = std::getenv(name);
+    if (env && !strcmp(env, "nt")) return true;
+    if (env && !strcmp(env, "memcpy")) return false;
+    return dflt;
+}
+const bool g_copy_in_nt = copy_flavour_nt("CN_HOST_COPY_IN", false);
+const bool g_copy_out_nt = copy_flavour_nt("CN_HOST_COPY_OUT", true);
+inline void staging_copy(uint8_t *dst, const uint8_t *src, size_t bytes, bool nt)
+{
+    if (nt) copy_nt_avx2(dst, src, bytes);
     else memcpy(dst, src, bytes);
 }
 
 // ------------------------------------------------------------------------------------------------
 // staging copier.  Pageable caller memory cannot be DMA'd, so it is copied through pinned staging by a small
-// process-wide pool (CN_HOST_THREADS / cn_set_host_threads, default min(8, cores/2) including the caller).
+// process-wide pool (CN_HOST_THREADS / cn_set_host_threads, default min(12, 5/8 of the cores) including the caller: the
+// measured optimum on a 16-vCPU box is 10 -- fewer cannot feed the PCIe link, more take host memory bandwidth away
+// from the DMA engines).
 // post() queues the slices of one copy and returns at once; wait() blocks until they are done and lets the
 // waiting thread execute queued slices itself.  The pool is created on first use and intentionally never
 // destroyed (its threads only ever wait on a condition variable).
@@ -77,7 +88,7 @@ public:
     }
 
     // queue dst <- src as slices of at most `slice` bytes
-    void post(Job &job, void *dst, const void *src, size_t bytes, size_t slice = kSlice)
+    void post(Job &job, void *dst, const void *src, size_t bytes, bool nt, size_t slice = kSlice)
     {
         if (bytes == 0) return;
         ensure_threads();
@@ -85,11 +96,23 @@ public:
             std::lock_guard<std::mutex> lk(mu_);
             for (size_t off = 0; off < bytes; off += slice) {
                 size_t n = bytes - off < slice ? bytes - off : slice;
-                queue_.push_back(Task{static_cast<uint8_t *>(dst) + off, static_cast<const uint8_t *>(src) + off, n, &job});
+                queue_.push_back(Task{static_cast<uint8_t *>(dst) + off, static_cast<const uint8_t *>(src) + off, n, &job, nullptr, nullptr, nt ? (size_t)1 : 0, 0});
                 job.pending++;
             }
         }
         cv_.notify_all();
+    }
+
+    // queue fn(ctx, a, b): an arbitrary piece of staging work (the gather / scatter of a batch of small sequences)
+    void post_fn(Job &job, void (*fn)(void *, size_t, size_t), void *ctx, size_t a, size_t b)
+    {
+        ensure_threads();
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            queue_.push_back(Task{nullptr, nullptr, 0, &job, fn, ctx, a, b});
+            job.pending++;
+        }
+        cv_.notify_one();
     }
 
     // returns when every slice posted on `job` has been copied; the caller copies slices too while it waits
@@ -101,7 +124,7 @@ public:
                 Task t = queue_.front();
                 queue_.pop_front();
                 lk.unlock();
-                staging_copy(t.dst, t.src, t.bytes);
+                t.run();
                 lk.lock();
                 if (--t.job->pending == 0) done_cv_.notify_all();
             } else {
@@ -119,7 +142,11 @@ public:
     static constexpr size_t kSlice = (size_t)512 << 10;
 
 private:
-    struct Task { uint8_t *dst; const uint8_t *src; size_t bytes; Job *job; };
+    struct Task {
+        uint8_t *dst; const uint8_t *src; size_t bytes; Job *job;
+        void (*fn)(void *, size_t, size_t); void *ctx; size_t a, b;
+        void run() const { if (fn) fn(ctx, a, b); else staging_copy(dst, src, bytes, a != 0); }     // a: streaming-store flag of a plain copy
+    };
 
     CopyPool() = default;
 
@@ -131,7 +158,7 @@ private:
         }
         if (n <= 0) {
             unsigned hc = std::thread::hardware_concurrency();
-            n = (int)(hc / 2 > 8 ? 8 : hc / 2);
+            n = (int)(hc * 5 / 8 > 12 ? 12 : hc * 5 / 8);
         }
         if (n < 1) n = 1;
         if (n > 64) n = 64;
@@ -156,7 +183,7 @@ private:
             Task t = queue_.front();
             queue_.pop_front();
             lk.unlock();
-            staging_copy(t.dst, t.src, t.bytes);
+            t.run();
             lk.lock();
             if (--t.job->pending == 0) done_cv_.notify_all();
         }
@@ -428,7 +455,7 @@ int host_codec_one(const Codec &cd, bool encode, const uint8_t *src, uint8_t *ds
     int first_error = CN_OK;
     auto post_in = [&](size_t k) {
         Slot &sl = p.slot[k % kSlots];
-        if (!src_pinned) { Geo g = geo(k); pool.post(sl.in_job, pin_in(sl), src + g.in_off, g.in_bytes); }
+        if (!src_pinned) { Geo g = geo(k); pool.post(sl.in_job, pin_in(sl), src + g.in_off, g.in_bytes, g_copy_in_nt); }
         sl.in_posted = true;
     };
     auto retire = [&](size_t k) -> int {                              // wait for chunk k's DMA, start copying its result out
@@ -436,7 +463,7 @@ int host_codec_one(const Codec &cd, bool encode, const uint8_t *src, uint8_t *ds
         cudaError_t e = cudaEventSynchronize(sl.done);
         sl.issued = false;
         if (e != cudaSuccess) return fail(CN_ERR_CUDA, "host pipeline: chunk %zu failed: %s", k, cudaGetErrorString(e));
-        if (!dst_pinned) { Geo g = geo(k); pool.post(sl.out_job, dst + g.out_off, pin_out(sl), g.out_bytes); }
+        if (!dst_pinned) { Geo g = geo(k); pool.post(sl.out_job, dst + g.out_off, pin_out(sl), g.out_bytes, g_copy_out_nt); }
         return CN_OK;
     };
     // retire, in order, every ISSUED chunk whose event has completed (block_first: wait for the oldest one)
@@ -502,6 +529,145 @@ int host_codec_one(const Codec &cd, bool encode, const uint8_t *src, uint8_t *ds
     }
     if (first_error != CN_OK) { cudaGetLastError(); return first_error; }
     return finish_counted(slots_used);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Many independent small sequences in ONE call (cn_n_to_bits_host_batch / cn_bits_to_n_host_batch).  One call per
+// read is launch-latency-bound on a GPU (16 us for the reference's own 40 000-nt bench shape, SURVEY 7 hard part 3);
+// here the sequences are laid end to end in pinned staging, each padded to a whole word with zero bytes (code 0, so
+// every sequence's last word gets the zero high bits the contract asks for), and ONE ordinary encode / decode launch
+// covers thousands of them.  Gather and scatter are spread over the copier pool; chunks flow through the same ring.
+// ------------------------------------------------------------------------------------------------
+struct BatchCtx {
+    bool encode;
+    const void *const *in;
+    void *const *out;
+    const size_t *lens;
+    const size_t *woff;                   // word offset of every sequence inside its chunk
+    uint8_t *pin_big, *pin_small;
+};
+void batch_gather(void *c, size_t a, size_t b)
+{
+    const BatchCtx &x = *static_cast<const BatchCtx *>(c);
+    for (size_t i = a; i < b; i++) {
+        const size_t len = x.lens[i];
+        if (!len) continue;
+        if (x.encode) {
+            uint8_t *dst = x.pin_big + x.woff[i] * 32;
+            memcpy(dst, x.in[i], len);
+            if (len & 31) memset(dst + len, 0, 32 - (len & 31));
+        } else {
+            memcpy(x.pin_small + x.woff[i] * 8, x.in[i], ((len + 31) >> 5) * 8);
+        }
+    }
+}
+void batch_scatter(void *c, size_t a, size_t b)
+{
+    const BatchCtx &x = *static_cast<const BatchCtx *>(c);
+    for (size_t i = a; i < b; i++) {
+        const size_t len = x.lens[i];
+        if (!len) continue;
+        if (x.encode) memcpy(x.out[i], x.pin_small + x.woff[i] * 8, ((len + 31) >> 5) * 8);
+        else memcpy(x.out[i], x.pin_big + x.woff[i] * 32, len);
+    }
+}
+
+int host_batch_one(bool encode, const void *const *in, const size_t *lens, size_t count, void *const *out)
+{
+    HostPipe &p = t_pipe;
+    int rc = pipe_prepare(p);
+    if (rc != CN_OK) return rc;
+    CopyPool &pool = CopyPool::get();
+    const Codec &cd = kCodec2bit;
+    const size_t stage = g_host_chunk_pageable.load(std::memory_order_relaxed);
+    const size_t stage_words = stage / 32;
+
+    // plan: consecutive sequences are grouped into chunks of at most `stage` padded bytes; a sequence that does not fit a
+    // chunk on its own goes through the ordinary streaming path afterwards
+    struct Chunk { size_t i0, i1, words; };
+    std::vector<Chunk> chunks;
+    std::vector<size_t> woff(count), big;
+    Chunk cur{0, 0, 0};
+    for (size_t i = 0; i < count; i++) {
+        const size_t w = (lens[i] + 31) >> 5;
+        if (lens[i] && (!in[i] || !out[i])) return fail(CN_ERR_ARG, "batch: null pointer for sequence %zu", i);
+        if (w > stage_words) {
+            big.push_back(i);
+            woff[i] = 0;
+            // a big sequence still ends the running chunk so that chunks stay ranges of consecutive indices
+            if (cur.i1 > cur.i0) chunks.push_back(cur);
+            cur = Chunk{i + 1, i + 1, 0};
+            continue;
+        }
+        if (cur.words + w > stage_words) {
+            chunks.push_back(cur);
+            cur = Chunk{i, i, 0};
+        }
+        woff[i] = cur.words;
+        cur.words += w;
+        cur.i1 = i + 1;
+    }
+    if (cur.i1 > cur.i0) chunks.push_back(cur);
+
+    const size_t nchunks = chunks.size();
+    const int slots_used = nchunks < (size_t)kSlots ? (int)nchunks : kSlots;
+    for (int k = 0; k < slots_used; k++)
+        if ((rc = slot_ensure(p.slot[k], stage, true, true)) != CN_OK) return rc;
+    std::vector<BatchCtx> ctx(slots_used ? slots_used : 1);
+
+    // gather / scatter of one chunk, cut into pool tasks of >= 128 KiB of payload
+    auto post_ranges = [&](CopyPool::Job &job, void (*fn)(void *, size_t, size_t), BatchCtx *c, const Chunk &ch) {
+        size_t a = ch.i0, acc = 0;
+        for (size_t i = ch.i0; i < ch.i1; i++) {
+            acc += lens[i];
+            if (acc >= ((size_t)128 << 10) || i + 1 == ch.i1) { pool.post_fn(job, fn, c, a, i + 1); a = i + 1; acc = 0; }
+        }
+    };
+    int first_error = CN_OK;
+    auto scatter_chunk = [&](size_t k) -> int {                       // wait for chunk k's DMA, start scattering its result
+        Slot &sl = p.slot[k % kSlots];
+        cudaError_t e = cudaEventSynchronize(sl.done);
+        if (e != cudaSuccess) return fail(CN_ERR_CUDA, "batch pipeline: chunk %zu failed: %s", k, cudaGetErrorString(e));
+        post_ranges(sl.out_job, batch_scatter, &ctx[k % kSlots], chunks[k]);
+        return CN_OK;
+    };
+    for (size_t k = 0; k < nchunks; k++) {
+        Slot &sl = p.slot[k % kSlots];
+        if (k >= (size_t)kSlots) {
+            if ((rc = scatter_chunk(k - kSlots)) != CN_OK) { first_error = rc; break; }
+            pool.wait(sl.out_job);                                    // the slot's context is about to be rewritten
+        }
+        ctx[k % kSlots] = BatchCtx{encode, in, out, lens, woff.data(), sl.pin_big, sl.pin_small};
+        post_ranges(sl.in_job, batch_gather, &ctx[k % kSlots], chunks[k]);
+        pool.wait(sl.in_job);
+        const size_t words = chunks[k].words, nt = words * 32;
+        uint8_t *h_in = encode ? sl.pin_big : sl.pin_small, *h_out = encode ? sl.pin_small : sl.pin_big;
+        uint8_t *d_in = encode ? sl.dev_big : sl.dev_small, *d_out = encode ? sl.dev_small : sl.dev_big;
+        const size_t in_bytes = encode ? nt : words * 8, out_bytes = encode ? words * 8 : nt;
+        cudaError_t e = cudaMemcpyAsync(d_in, h_in, in_bytes, cudaMemcpyHostToDevice, sl.stream);
+        rc = e != cudaSuccess ? CN_OK
+             : (encode ? cd.enc(d_in, nt, d_out, cn::kEncPlain, nullptr, sl.stream) : cd.dec(d_in, words, nt, d_out, sl.stream));
+        if (e == cudaSuccess && rc == CN_OK) e = cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, sl.stream);
+        if (e == cudaSuccess && rc == CN_OK) e = cudaEventRecord(sl.done, sl.stream);
+        if (e != cudaSuccess) rc = fail(CN_ERR_CUDA, "batch pipeline: submitting chunk %zu failed: %s", k, cudaGetErrorString(e));
+        if (rc != CN_OK) { first_error = rc; break; }
+    }
+    if (first_error == CN_OK) {
+        for (size_t k = nchunks > (size_t)kSlots ? nchunks - kSlots : 0; k < nchunks; k++)
+            if ((rc = scatter_chunk(k)) != CN_OK) { first_error = rc; break; }
+    }
+    for (int k = 0; k < slots_used; k++) {
+        if (first_error != CN_OK) cudaStreamSynchronize(p.slot[k].stream);
+        pool.wait(p.slot[k].in_job);
+        pool.wait(p.slot[k].out_job);
+    }
+    if (first_error != CN_OK) { cudaGetLastError(); return first_error; }
+    for (size_t i : big) {
+        const size_t len = lens[i];
+        rc = host_codec_one(cd, encode, static_cast<const uint8_t *>(in[i]), static_cast<uint8_t *>(out[i]), len, HostMode{});
+        if (rc != CN_OK) return rc;
+    }
+    return CN_OK;
 }
 
 }  // namespace

@@ -21,7 +21,7 @@ from ._lib import LengthError, check
 
 __all__ = [
     "n_to_bits_cuda", "bits_to_n_cuda", "words_for_len", "n_to_bits_checked_cuda", "encode_checked_device",
-    "n_to_bits_lut_cuda", "n_to_bits_ex_cuda", "encode_ex_device",
+    "n_to_bits_lut_cuda", "n_to_bits_ex_cuda", "encode_ex_device", "n_to_bits_batch_cuda", "bits_to_n_batch_cuda",
     "encode_device", "decode_device", "generate_device", "generate_words_device", "LengthError",
     "ENC_PLAIN", "ENC_COUNT", "ENC_LUT_EXACT",
 ]
@@ -75,6 +75,47 @@ def n_to_bits_ex_cuda(n, mode: int):
 def n_to_bits_lut_cuda(n) -> np.ndarray:
     """Bit-exact n_to_bits_lut (src/n_to_bits.rs:34-47) on EVERY input, including bytes outside the alphabet (-> 0)."""
     return n_to_bits_ex_cuda(n, ENC_LUT_EXACT)[0]
+
+
+def _ptr_array(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_void_p))
+
+
+def n_to_bits_batch_cuda(buf, offsets):
+    """Encode many independent sequences in ONE call (cn_n_to_bits_host_batch).  Sequence i is buf[offsets[i]:offsets[i+1]]
+    (offsets: count+1 non-decreasing integers).  Returns (words, word_offsets): sequence i's packed words -- exactly what
+    n_to_bits_cuda(sequence i) returns -- are words[word_offsets[i]:word_offsets[i+1]]."""
+    src = _as_u8(buf)
+    offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+    count = offs.size - 1
+    lens = np.ascontiguousarray(np.diff(offs))
+    wcount = (lens + np.uint64(31)) >> np.uint64(5)
+    woffs = np.zeros(count + 1, dtype=np.uint64)
+    np.cumsum(wcount, out=woffs[1:])
+    words = np.empty(int(woffs[-1]), dtype=np.uint64)
+    in_ptrs = np.uint64(src.ctypes.data) + offs[:-1]
+    out_ptrs = np.uint64(words.ctypes.data) + woffs[:-1] * np.uint64(8)
+    lens_c = lens.ctypes.data_as(ctypes.POINTER(ctypes.c_size_t))
+    check(_lib.load().cn_n_to_bits_host_batch(_ptr_array(in_ptrs), lens_c, count, _ptr_array(out_ptrs)))
+    return words, woffs
+
+
+def bits_to_n_batch_cuda(words, word_offsets, lengths):
+    """Inverse of n_to_bits_batch_cuda: returns (buf, offsets) with sequence i at buf[offsets[i]:offsets[i+1]]."""
+    w = np.ascontiguousarray(words, dtype=np.uint64)
+    woffs = np.ascontiguousarray(word_offsets, dtype=np.uint64)
+    lens = np.ascontiguousarray(lengths, dtype=np.uint64)
+    count = lens.size
+    if np.any(lens > (np.diff(woffs) << np.uint64(5))):
+        raise LengthError(_lib.CN_ERR_LENGTH, _lib.load().cn_length_panic_message().decode())
+    offs = np.zeros(count + 1, dtype=np.uint64)
+    np.cumsum(lens, out=offs[1:])
+    out = np.empty(int(offs[-1]), dtype=np.uint8)
+    in_ptrs = np.uint64(w.ctypes.data) + woffs[:-1] * np.uint64(8)
+    out_ptrs = np.uint64(out.ctypes.data) + offs[:-1]
+    lens_c = lens.ctypes.data_as(ctypes.POINTER(ctypes.c_size_t))
+    check(_lib.load().cn_bits_to_n_host_batch(_ptr_array(in_ptrs), lens_c, count, _ptr_array(out_ptrs)))
+    return out, offs
 
 
 def bits_to_n_cuda(bits, length: int) -> bytes:

@@ -77,28 +77,95 @@ def assemble_packed(local_words, total_len: int, group=None, granule: int = GRAN
     return full
 
 
-def encode_sharded(n_shard, total_len: int, group=None, assemble: bool = False, granule: int = GRANULE):
-    """Encode this rank's shard on its GPU (cn_encode_device through the C ABI); optionally assemble."""
-    import torch.distributed as dist
-    from . import n_to_bits
+# The base-5 tiled decode wants its packed input 32-byte aligned: shard boundaries that are multiples of 4 words (108 nt)
+# keep every rank's slice of the assembled tensor on the fast path.
+BASE5_ALIGNED_GRANULE = 27 * 4
 
+
+def _codec(codec: str):
+    """(nucleotides per word, encode, decode) of "2bit" (n_to_bits) or "base5" (n_to_bits2)."""
+    from . import n_to_bits, n_to_bits2
+    if codec == "2bit":
+        return GROUP_2BIT, n_to_bits.encode_device, n_to_bits.decode_device
+    if codec == "base5":
+        return GROUP_BASE5, n_to_bits2.encode2_device, n_to_bits2.decode2_device
+    raise ValueError("codec must be '2bit' or 'base5'")
+
+
+def default_granule(codec: str) -> int:
+    return GRANULE if codec == "2bit" else BASE5_ALIGNED_GRANULE
+
+
+def encode_sharded(n_shard, total_len: int, group=None, assemble: bool = False, granule: int = None, codec: str = "2bit"):
+    """Encode this rank's shard on its GPU (cn_encode_device / cn_encode2_device through the C ABI); optionally assemble."""
+    import torch.distributed as dist
+
+    grp, enc, _ = _codec(codec)
+    granule = default_granule(codec) if granule is None else granule
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    start, end = shard_bounds(total_len, world, rank, granule)
+    start, end = shard_bounds(total_len, world, rank, granule, grp)
     if n_shard.numel() != end - start:
         raise ValueError(f"rank {rank}: shard must hold nucleotides [{start}, {end})")
-    words = n_to_bits.encode_device(n_shard)
-    return assemble_packed(words, total_len, group, granule) if assemble else words
+    words = enc(n_shard)
+    return assemble_packed(words, total_len, group, granule, grp) if assemble else words
 
 
-def decode_sharded(full_words, total_len: int, group=None, granule: int = GRANULE):
+def decode_sharded(full_words, total_len: int, group=None, granule: int = None, codec: str = "2bit"):
     """Decode this rank's range of a packed tensor every rank already holds (e.g. after assemble/broadcast)."""
     import torch.distributed as dist
-    from . import n_to_bits
+
+    grp, _, dec = _codec(codec)
+    granule = default_granule(codec) if granule is None else granule
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    start, end = shard_bounds(total_len, world, rank, granule, grp)
+    ws, we = word_bounds(total_len, world, rank, granule, grp)
+    return dec(full_words[ws:we], end - start)
+
+
+def gather_packed(local_words, total_len: int, root: int = 0, group=None, granule: int = GRANULE, codec_group: int = GROUP_2BIT):
+    """Gather-to-root of the packed shards (the collective north_star names): `root` returns the full tensor, the
+    other ranks None.  NCCL: grouped send/recv; gloo: the same calls on CPU tensors."""
+    import torch
+    import torch.distributed as dist
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    start, end = shard_bounds(total_len, world, rank, granule)
-    ws, we = word_bounds(total_len, world, rank, granule)
-    return n_to_bits.decode_device(full_words[ws:we], end - start)
+    spans = [word_bounds(total_len, world, r, granule, codec_group) for r in range(world)]
+    if local_words.numel() != spans[rank][1] - spans[rank][0]:
+        raise ValueError(f"rank {rank}: expected {spans[rank][1] - spans[rank][0]} words, got {local_words.numel()}")
+    if rank != root:
+        if local_words.numel():
+            dist.send(local_words.contiguous(), dst=root, group=group)
+        return None
+    full = torch.empty(words_for_len(total_len, codec_group), dtype=local_words.dtype, device=local_words.device)
+    s, e = spans[root]
+    full[s:e] = local_words
+    reqs = [dist.irecv(full[s:e], src=r, group=group) for r, (s, e) in enumerate(spans) if r != root and e > s]
+    for q in reqs:
+        q.wait()
+    return full
+
+
+def scatter_packed(full_words, total_len: int, root: int = 0, group=None, granule: int = GRANULE, codec_group: int = GROUP_2BIT,
+                   like=None):
+    """Scatter of the packed words from `root` (which holds `full_words`): every rank returns its own word range.
+    `like` gives dtype/device on the non-root ranks."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    spans = [word_bounds(total_len, world, r, granule, codec_group) for r in range(world)]
+    s, e = spans[rank]
+    if rank == root:
+        reqs = [dist.isend(full_words[a:b].contiguous(), dst=r, group=group) for r, (a, b) in enumerate(spans) if r != root and b > a]
+        mine = full_words[s:e].clone()
+        for q in reqs:
+            q.wait()
+        return mine
+    ref = like if like is not None else full_words
+    mine = torch.empty(e - s, dtype=ref.dtype, device=ref.device)
+    if e > s:
+        dist.recv(mine, src=root, group=group)
+    return mine
 
 
 class PeerAssembly:
@@ -142,24 +209,27 @@ class PeerAssembly:
             self.peer_ptrs.append(p.value)
         dist.barrier(group=group)
 
-    def encode(self, n_shard, stream=None):
-        """Launch the fused kernel for this rank's shard (asynchronous)."""
+    def encode(self, n_shard, stream=None, dests=None):
+        """Launch the fused kernel for this rank's shard (asynchronous).  `dests` = ranks whose buffers receive the packed
+        words: all of them by default (encode + all-gather), `[root]` for encode + gather-to-root."""
         torch, ctypes = self._torch, self._ctypes
         start, end = shard_bounds(self.total_len, self.world, self.rank, self.granule)
         if n_shard.numel() != end - start or n_shard.dtype != torch.uint8 or not n_shard.is_cuda:
             raise ValueError(f"rank {self.rank}: shard must be the uint8 CUDA tensor of nucleotides [{start}, {end})")
         word_off = (start >> 5) * 8
-        outs = (ctypes.c_void_p * self.world)(*[p + word_off for p in self.peer_ptrs])
+        ranks = list(range(self.world)) if dests is None else list(dests)
+        outs = (ctypes.c_void_p * len(ranks))(*[self.peer_ptrs[r] + word_off for r in ranks])
         s = stream if stream is not None else torch.cuda.current_stream()
-        self._lib.check(self.lib.cn_encode_multi_device(n_shard.data_ptr(), end - start, outs, self.world, s.cuda_stream))
+        self._lib.check(self.lib.cn_encode_multi_device(n_shard.data_ptr(), end - start, outs, len(ranks), s.cuda_stream))
 
-    def decode_from(self, source_rank: int, stream=None):
+    def decode_from(self, source_rank: int, stream=None, out=None):
         """Scatter/broadcast + decode in one kernel: decode THIS rank's range of the packed sequence reading the words
         straight out of `source_rank`'s buffer (peer loads over NVLink) -- no copy of the packed words first."""
         torch = self._torch
         start, end = shard_bounds(self.total_len, self.world, self.rank, self.granule)
         ws, we = word_bounds(self.total_len, self.world, self.rank, self.granule)
-        out = torch.empty(end - start, dtype=torch.uint8, device="cuda")
+        if out is None:
+            out = torch.empty(end - start, dtype=torch.uint8, device="cuda")
         s = stream if stream is not None else torch.cuda.current_stream()
         self._lib.check(self.lib.cn_decode_device(self.peer_ptrs[source_rank] + ws * 8, we - ws, end - start,
                                                   out.data_ptr(), s.cuda_stream))

@@ -76,6 +76,14 @@ CN_API int cn_n_to_bits_host(const uint8_t *n, size_t len, uint64_t *out);
  * Returns CN_ERR_LENGTH when len > 32 * nwords. */
 CN_API int cn_bits_to_n_host(const uint64_t *bits, size_t nwords, size_t len, uint8_t *out);
 
+/* Many independent sequences in ONE call.  The reference's own bench shape (40 000 nt, benches/bench_n_to_bits.rs:10,
+ * 38-39) is launch-latency-bound on a GPU one call at a time; here sequence i -- seqs[i][0 .. lens[i]) -- is encoded into
+ * outs[i][0 .. cn_words_for_len(lens[i])) exactly as cn_n_to_bits_host would, but thousands of sequences share one kernel
+ * launch and one pair of PCIe transfers.  The inverse decodes lens[i] nucleotides from bits[i] (which must hold
+ * cn_words_for_len(lens[i]) words) into outs[i].  Zero-length sequences are skipped (their pointers may be NULL). */
+CN_API int cn_n_to_bits_host_batch(const uint8_t *const *seqs, const size_t *lens, size_t count, uint64_t *const *outs);
+CN_API int cn_bits_to_n_host_batch(const uint64_t *const *bits, const size_t *lens, size_t count, uint8_t *const *outs);
+
 /* ---- device-resident entry points (the roofline path; buffers already in HBM) ------------------ */
 /* `stream` is a cudaStream_t (NULL = default stream); launches are asynchronous on it, on the current
  * device.  d_n may have any alignment (16-byte aligned input takes the fast path); d_out must be 8-byte
@@ -203,7 +211,7 @@ CN_API int cn_set_host_strategy(int strategy, size_t chunk_bytes);
  * ones staged in pageable_chunk pieces.  cn_set_host_strategy's chunk_bytes sets both. */
 CN_API int cn_set_host_chunks(size_t pinned_chunk, size_t pageable_chunk);
 /* Threads that copy pageable caller memory to / from pinned staging (the waiting caller included).  0 = default:
- * CN_HOST_THREADS, else min(8, cores/2).  The pool only grows; a lower value takes effect for new pools only. */
+ * CN_HOST_THREADS, else min(12, 5/8 of the cores).  The pool only grows; a lower value takes effect for new pools only. */
 CN_API int cn_set_host_threads(int threads);
 
 #ifdef __cplusplus

@@ -20,6 +20,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <pthread.h>
 #include <immintrin.h>
 
@@ -319,6 +320,35 @@ CN_EXPORT int oracle_decode_mt(int kind, const uint64_t *bits, size_t nwords, si
     if (kind != 1 && kind != 3) return 3;
     if (len > (nwords << 5)) return 1;
     return run_sharded(kind, bits, out, len, threads);
+}
+
+/* The reference's own bench shape: one call per sequence, single thread, the output allocated inside the timed
+ * region (benches/bench_n_to_bits.rs:6-7, 15-19, 44-47).  Sequence i is buf[offsets[i] .. offsets[i+1]); `reps` passes over
+ * all of them; encode with n_to_bits_movemask then (roundtrip != 0) decode with bits_to_n_shuffle.  Returns seconds. */
+CN_EXPORT double oracle_time_small_calls(const uint8_t *buf, const uint64_t *offsets, size_t count, int reps, int roundtrip)
+{
+    struct timespec t0, t1;
+    volatile uint64_t sink = 0;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int r = 0; r < reps; r++) {
+        for (size_t i = 0; i < count; i++) {
+            const size_t len = (size_t)(offsets[i + 1] - offsets[i]);
+            const size_t words = oracle_words_for_len(len);
+            uint64_t *w = malloc((words ? words : 1) * 8);
+            oracle_n_to_bits_movemask(buf + offsets[i], len, w);
+            if (roundtrip) {
+                uint8_t *o = aligned_alloc(32, (words ? words : 1) * 32);       /* the SIMD decoder writes whole words (:271-272) */
+                oracle_bits_to_n_shuffle(w, words, len, o);
+                sink += o[0];
+                free(o);
+            }
+            sink += w[0];
+            free(w);
+        }
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    (void)sink;
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -31,7 +31,15 @@ pub mod ffi {
         pub fn cn_n_to_bits2_host(n: *const u8, len: usize, out: *mut u64) -> c_int;
         pub fn cn_bits_to_n2_host(bits: *const u64, nwords: usize, len: usize, out: *mut u8) -> c_int;
         pub fn cn_words2_for_len(len: usize) -> usize;
+        // ABI v2
+        pub fn cn_n_to_bits_ex_host(n: *const u8, len: usize, out: *mut u64, mode: c_int, invalid_count: *mut u64) -> c_int;
+        pub fn cn_n_to_bits_host_batch(seqs: *const *const u8, lens: *const usize, count: usize, outs: *const *mut u64) -> c_int;
+        pub fn cn_bits_to_n_host_batch(bits: *const *const u64, lens: *const usize, count: usize, outs: *const *mut u8) -> c_int;
+        pub fn cn_set_devices(devices: *const c_int, count: c_int) -> c_int;
+        pub fn cn_hamming_host(a: *const u64, b: *const u64, nwords: usize, len: usize, result: *mut u64) -> c_int;
+        pub fn cn_reverse_complement_host(bits: *const u64, nwords: usize, len: usize, out: *mut u64) -> c_int;
     }
+    pub const CN_ENC_LUT_EXACT: c_int = 2;
 }
 
 fn fail(status: c_int) -> ! {
@@ -55,6 +63,49 @@ pub fn n_to_bits_cuda(n: &[u8]) -> Vec<u64> {
         res.set_len(words);
     }
     res
+}
+
+/// Like `n_to_bits_cuda`, but bytes outside `{A,C,G,T,U,a,c,g,t,u}` encode as 0 exactly as `n_to_bits_lut`'s `BYTE_LUT` does
+/// (`src/n_to_bits.rs:8-21`), so the result equals `n_to_bits_lut(n)` on EVERY input.  Also returns how many such bytes there were.
+pub fn n_to_bits_lut_cuda(n: &[u8]) -> (Vec<u64>, u64) {
+    let words = (n.len() >> 5) + if n.len() & 31 == 0 { 0 } else { 1 };
+    let mut res: Vec<u64> = Vec::with_capacity(words);
+    let mut invalid = 0u64;
+    unsafe {
+        let status = ffi::cn_n_to_bits_ex_host(n.as_ptr(), n.len(), res.as_mut_ptr(), ffi::CN_ENC_LUT_EXACT, &mut invalid);
+        if status != ffi::CN_OK {
+            fail(status);
+        }
+        res.set_len(words);
+    }
+    (res, invalid)
+}
+
+/// Many independent sequences in ONE call (one kernel launch for thousands of reads): element `i` of the result is
+/// exactly `n_to_bits_cuda(seqs[i])`.
+pub fn n_to_bits_cuda_batch(seqs: &[&[u8]]) -> Vec<Vec<u64>> {
+    let lens: Vec<usize> = seqs.iter().map(|s| s.len()).collect();
+    let ins: Vec<*const u8> = seqs.iter().map(|s| s.as_ptr()).collect();
+    let mut res: Vec<Vec<u64>> = lens.iter().map(|&l| Vec::with_capacity((l >> 5) + if l & 31 == 0 { 0 } else { 1 })).collect();
+    let outs: Vec<*mut u64> = res.iter_mut().map(|v| v.as_mut_ptr()).collect();
+    unsafe {
+        let status = ffi::cn_n_to_bits_host_batch(ins.as_ptr(), lens.as_ptr(), seqs.len(), outs.as_ptr());
+        if status != ffi::CN_OK {
+            fail(status);
+        }
+        for (v, &l) in res.iter_mut().zip(lens.iter()) {
+            v.set_len((l >> 5) + if l & 31 == 0 { 0 } else { 1 });
+        }
+    }
+    res
+}
+
+/// Fan every later `*_cuda` call out over these GPUs (one PCIe link each); an empty slice restores single-GPU behaviour.
+pub fn set_devices(devices: &[i32]) {
+    let status = unsafe { ffi::cn_set_devices(devices.as_ptr(), devices.len() as c_int) };
+    if status != ffi::CN_OK {
+        fail(status);
+    }
 }
 
 /// Decode pairs of bits from packed 64-bit integers to get a byte string of `{A, T, C, G}`, on a B200.

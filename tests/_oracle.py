@@ -49,6 +49,8 @@ class Oracle:
         L.oracle_count_invalid2.argtypes = [c_void_p, c_size_t]
         L.oracle_hamming.restype, L.oracle_hamming.argtypes = c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]
         L.oracle_complement.restype, L.oracle_complement.argtypes = c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_int]
+        L.oracle_time_small_calls.restype = ctypes.c_double
+        L.oracle_time_small_calls.argtypes = [c_void_p, c_void_p, c_size_t, c_int, c_int]
         L.oracle_cpu_ok.restype = c_int
         L.oracle_words2_for_len.restype, L.oracle_words2_for_len.argtypes = c_size_t, [c_size_t]
         for v in ENCODERS2:
@@ -148,6 +150,12 @@ class Oracle:
         if rc == 1:
             raise ValueError("The length is greater than the number of nucleotides!")
         return out
+
+    def time_small_calls(self, buf, offsets, reps: int = 1, roundtrip: bool = True) -> float:
+        """seconds for `reps` passes of one-call-per-sequence movemask (+ shuffle) on ONE thread, allocation inside"""
+        a = self._u8(buf)
+        o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        return float(self.lib.oracle_time_small_calls(a.ctypes.data, o.ctypes.data, o.size - 1, reps, int(roundtrip)))
 
     def count_invalid2(self, n) -> int:
         a = self._u8(n)

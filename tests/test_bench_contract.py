@@ -23,6 +23,11 @@ def test_reference_arm_line():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert "workload" in line["config"] and line["vs_baseline"] is None and line["dtype"] == "u8"
+    # the config object is built by ONE function for both arms, so the driver's same_config check can hold
+    import argparse
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.shared_config(argparse.Namespace(nucleotides=1 << 22, alphabet=10))
 
 
 def test_non_zero_rank_of_reference_arm_is_silent():

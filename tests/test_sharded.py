@@ -73,6 +73,14 @@ def _worker(rank, world, port, total, granule, result_dir):
         ws, we = sharded.word_bounds(total, world, rank, granule)
         dec = orc.bits_to_n(full.numpy().view(np.uint64)[ws:we], end - start, "lut")
         ok = ok and dec == orc.canonical(shard)
+        # gather-to-root and scatter (the collectives north_star names), both roots
+        for root in (0, world - 1):
+            gathered = sharded.gather_packed(local, total, root=root, granule=granule)
+            ok = ok and ((gathered is None) == (rank != root))
+            if rank == root:
+                ok = ok and np.array_equal(gathered.numpy().view(np.uint64), whole)
+            mine = sharded.scatter_packed(gathered, total, root=root, granule=granule, like=local)
+            ok = ok and torch.equal(mine, local)
         open(os.path.join(result_dir, f"rank{rank}"), "w").write("ok" if ok else "mismatch")
     finally:
         dist.destroy_process_group()

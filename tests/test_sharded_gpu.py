@@ -38,6 +38,25 @@ def _worker(rank, world, port, total, granule, result_dir):
         ok = np.array_equal(full.cpu().numpy().view(np.uint64), orc.encode_mt(whole, "lut"))
         dec = sharded.decode_sharded(full, total, granule=granule)
         ok = ok and dec.cpu().numpy().tobytes() == orc.canonical(whole[start:end])
+        # gather-to-root / scatter over NCCL (the collectives north_star names), then decode what was scattered
+        ws, we = sharded.word_bounds(total, world, rank, granule)
+        for root in (0, world - 1):
+            gathered = sharded.gather_packed(full[ws:we].clone(), total, root=root, granule=granule)
+            if rank == root:
+                ok = ok and bool(torch.equal(gathered, full))
+            mine = sharded.scatter_packed(gathered, total, root=root, granule=granule, like=full)
+            ok = ok and bool(torch.equal(mine, full[ws:we]))
+            ok = ok and cn.decode_device(mine, end - start).cpu().numpy().tobytes() == orc.canonical(whole[start:end])
+        # the base-5 codec through the same sharded entry points (27-nt words; granule keeps word slices 32-byte aligned)
+        total5 = total // 3 + 7
+        g5 = sharded.default_granule("base5") * 64
+        s5, e5 = sharded.shard_bounds(total5, world, rank, g5, 27)
+        whole5 = orc.generate2(total5, seed=8, alphabet=12)
+        d5 = torch.from_numpy(whole5[s5:e5]).cuda()
+        full5 = sharded.encode_sharded(d5, total5, assemble=True, granule=g5, codec="base5")
+        ok = ok and np.array_equal(full5.cpu().numpy().view(np.uint64), orc.n_to_bits2(whole5, "lut"))
+        dec5 = sharded.decode_sharded(full5, total5, granule=g5, codec="base5")
+        ok = ok and dec5.cpu().numpy().tobytes() == orc.canonical2(whole5[s5:e5])
         open(os.path.join(result_dir, f"rank{rank}"), "w").write("ok" if ok else "mismatch")
     finally:
         dist.destroy_process_group()
@@ -123,6 +142,20 @@ def _fused_worker(rank, world, port, total, granule, result_dir):
         remote = asm.decode_from((rank + 1) % world)
         torch.cuda.synchronize()
         ok = ok and remote.cpu().numpy().tobytes() == orc.canonical(whole[start:end])
+        # encode + gather-to-ROOT only: every rank stores its words into the root's buffer and nowhere else
+        root = world - 1
+        asm.full.fill_(-1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        asm.encode(d_shard, dests=[root])
+        asm.finish()
+        if rank == root:
+            ok = ok and np.array_equal(asm.full.cpu().numpy().view(np.uint64), orc.encode_mt(whole, "lut"))
+        else:
+            ok = ok and bool((asm.full == -1).all())
+        scattered = asm.decode_from(root)                    # scatter + decode in one kernel, straight from the root
+        torch.cuda.synchronize()
+        ok = ok and scattered.cpu().numpy().tobytes() == orc.canonical(whole[start:end])
         asm.close()
         open(os.path.join(result_dir, f"rank{rank}"), "w").write("ok" if ok else "mismatch")
     finally:
