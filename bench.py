@@ -867,8 +867,10 @@ def run_e2e(args, cn, lib, _lib, torch, np, rank, local_rank, world, barrier, cp
     else:
         per_gpu = res["host_traffic_gbs"] / world
         res["limiter"] = (f"{world} links carried {res['host_traffic_gbs']:.0f} GB/s of host traffic in aggregate ({per_gpu:.0f} GB/s per GPU; "
-                          f"a lone link carries ~66 GB/s on this round trip): the box's host memory system / PCIe root complex, not the links, "
-                          "bounds the fanned-out call (tools/host_ceiling `pcie` section, profiles/host_ceiling_r02_n8.jsonl)")
+                          f"a lone link carries ~66 GB/s on this round trip).  Beyond 2 links the HOST side of the box is the bound, not the "
+                          "links or the GPUs: pure cudaMemcpyAsync from pinned memory tops out at 71 / 74 / 94 GB/s device-to-host and "
+                          "111 / 115 / 186 GB/s host-to-device over 2 / 4 / 8 links of the 8-GPU box (tools/host_ceiling `pcie`, "
+                          "profiles/host_ceiling_r02_n8.jsonl), which caps decode at ~90 Gnt/s and the round trip at ~60 Gnt/s")
     if note:
         res["note"] = note
     return res

@@ -33,6 +33,7 @@ PROTOTYPES = {
     "cn_encode_device": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "cn_decode_device": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
     "cn_encode_multi_device": (c_int, [c_void_p, c_size_t, POINTER(c_void_p), c_int, c_void_p]),
+    "cn_encode2_multi_device": (c_int, [c_void_p, c_size_t, POINTER(c_void_p), c_int, c_void_p]),
     "cn_ipc_export": (c_int, [c_void_p, c_void_p, POINTER(c_size_t)]),
     "cn_ipc_open": (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
     "cn_ipc_close": (c_int, [c_void_p, c_size_t]),

@@ -173,6 +173,10 @@ int cn_encode_multi_device(const void *d_n, size_t len, void *const *d_outs, int
 {
     return encode_multi_device(d_n, len, d_outs, nout, static_cast<cudaStream_t>(stream));
 }
+int cn_encode2_multi_device(const void *d_n, size_t len, void *const *d_outs, int nout, void *stream)
+{
+    return encode2_multi_device(d_n, len, d_outs, nout, static_cast<cudaStream_t>(stream));
+}
 int cn_ipc_export(void *d_ptr, void *handle64, size_t *offset) { return ipc_export(d_ptr, handle64, offset); }
 int cn_ipc_open(const void *handle64, size_t offset, void **d_ptr) { return ipc_open(handle64, offset, d_ptr); }
 int cn_ipc_close(void *d_ptr, size_t offset) { return ipc_close(d_ptr, offset); }

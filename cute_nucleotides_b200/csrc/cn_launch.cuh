@@ -217,6 +217,29 @@ int encode_multi_device(const void *d_n, size_t len, void *const *d_outs, int no
     return CN_OK;
 }
 
+// base-5 flavour of the above: d_n 16-byte aligned, destinations 32-byte aligned
+int encode2_multi_device(const void *d_n, size_t len, void *const *d_outs, int nout, cudaStream_t s)
+{
+    if (nout < 1 || nout > cn::kMaxPeers + 1 - 1 || !d_outs) return fail(CN_ERR_ARG, "cn_encode2_multi_device: 1..%d destinations", cn::kMaxPeers);
+    if (len == 0) return CN_OK;
+    if (!d_n || (addr(d_n) & 15)) return fail(CN_ERR_ARG, "cn_encode2_multi_device: input must be 16-byte aligned");
+    cn::PeerOuts64 more{};
+    for (int d = 0; d < nout; d++) {
+        if (!d_outs[d] || (addr(d_outs[d]) & 31)) return fail(CN_ERR_ARG, "cn_encode2_multi_device: destination %d null or not 32-byte aligned", d);
+        if (d > 0) more.p[d - 1] = static_cast<uint64_t *>(d_outs[d]);
+    }
+    const size_t total = len / 27 + ((len % 27) ? 1 : 0);
+    const size_t ntiles = (len / 27) / cn::kB5WarpWords;
+    const size_t blocks = (ntiles + 1 + cn::kB5Warps - 1) / cn::kB5Warps;
+    if (blocks > kMaxGrid) return fail(CN_ERR_ARG, "cn_encode2_multi_device: input too large for one launch");
+    cn::b5_encode_kernel<true, cn::kEncPlain, true><<<(unsigned)blocks, cn::kB5Warps * 32, 0, s>>>(
+        static_cast<const uint8_t *>(d_n), static_cast<uint64_t *>(d_outs[0]), len, ntiles, total, nullptr, more, nout - 1);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(CN_ERR_CUDA, "multi-destination base-5 encode launch failed: %s", cudaGetErrorString(e));
+    return CN_OK;
+}
+
 // ---- CUDA IPC: let another process (one process per GPU) map a buffer of this one -----------------------
 // cudaIpcGetMemHandle describes the whole ALLOCATION that contains a pointer; a tensor handed out by a caching
 // allocator may sit at an offset inside it, so the offset is exported alongside (cuMemGetAddressRange, resolved at

@@ -236,10 +236,13 @@ __device__ __forceinline__ void b5_decode_scalar(const uint64_t *__restrict__ bi
 // finishes words [ntiles*128, total_words) with the scalar path.  `in` must be 16-byte aligned when
 // ntiles > 0.
 // ------------------------------------------------------------------------------------------------------
-template <bool TMA, int MODE = kEncPlain>
+// more destinations of the same packed words (multi-GPU: peer-mapped buffers of the other ranks, see encode_multi_kernel)
+struct PeerOuts64 { uint64_t *p[kMaxPeers]; };
+
+template <bool TMA, int MODE = kEncPlain, bool MULTI = false>
 __global__ void __launch_bounds__(kB5Warps * 32)
 b5_encode_kernel(const uint8_t *__restrict__ in, uint64_t *__restrict__ out, size_t len, size_t ntiles, size_t total_words,
-                 unsigned long long *__restrict__ invalid_counter)
+                 unsigned long long *__restrict__ invalid_counter, PeerOuts64 more = PeerOuts64{}, int nmore = 0)
 {
     uint32_t n_invalid = 0;
     __shared__ __align__(128) uint8_t smem[kB5Warps * kB5SmemPerWarp];
@@ -286,8 +289,17 @@ b5_encode_kernel(const uint8_t *__restrict__ in, uint64_t *__restrict__ out, siz
         b5_pack108(d, w);
         st_stream32(out + g * kB5WarpWords + 4 * lane, make_uint4(w[0].x, w[0].y, w[1].x, w[1].y),
                     make_uint4(w[2].x, w[2].y, w[3].x, w[3].y));
+        if constexpr (MULTI) {
+#pragma unroll
+            for (int k = 0; k < kMaxPeers; k++)
+                if (k < nmore) st_stream32(more.p[k] + g * kB5WarpWords + 4 * lane, make_uint4(w[0].x, w[0].y, w[1].x, w[1].y),
+                                           make_uint4(w[2].x, w[2].y, w[3].x, w[3].y));
+        }
     } else if (g == ntiles) {
         n_invalid += b5_encode_scalar<MODE>(in, len, out, ntiles * kB5WarpWords, total_words, lane, 32);
+        if constexpr (MULTI) {
+            for (int k = 0; k < nmore; k++) b5_encode_scalar<kEncPlain>(in, len, more.p[k], ntiles * kB5WarpWords, total_words, lane, 32);
+        }
     }
     if constexpr (MODE != kEncPlain) { if (invalid_counter) report_invalid(invalid_counter, n_invalid); }
 }

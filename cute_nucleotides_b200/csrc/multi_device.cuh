@@ -160,6 +160,11 @@ private:
 
 // below this many nucleotides per device a call is not worth splitting further
 constexpr size_t kFanMinPerDevice = (size_t)8 << 20;
+const size_t g_fan_pageable_max = [] {
+    const char *env = std::getenv("CN_FANOUT_PAGEABLE_MAX");
+    long v = env ? std::atol(env) : 2;
+    return (size_t)(v < 1 ? 1 : v);
+}();
 
 // The host-slice entry points land here: one device -> host_codec_one on the calling thread; a device set -> fan out.
 int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, size_t len, const HostMode &mode = HostMode{})
@@ -170,6 +175,14 @@ int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, s
 
     size_t parts = len / kFanMinPerDevice;
     if (parts > devs.size()) parts = devs.size();
+    // Pageable caller buffers are staged by CPU copier threads, and those -- not the links -- are the bottleneck: every
+    // extra DMA stream takes host memory bandwidth away from them.  Measured with 8 links (profiles/bench_r02_n8*.json,
+    // tools/host_ceiling `mix`): 20 Gnt/s over 8 GPUs vs 33 Gnt/s over 2.  So a pageable call uses at most
+    // CN_FANOUT_PAGEABLE_MAX (default 2) devices.
+    if (parts > g_fan_pageable_max && len >= kFanMinPerDevice) {
+        const size_t nwords = cd.words(len);
+        if (!is_pinned(src, encode ? len : nwords * 8) || !is_pinned(dst, encode ? nwords * 8 : len)) parts = g_fan_pageable_max;
+    }
     if (parts < 1) parts = 1;
     // ranges are multiples of 1 Mi nucleotides (2-bit) / 256 warp tiles (base-5): whole words, whole chunk units, and
     // 128-byte aligned packed offsets

@@ -132,6 +132,57 @@ reverse_complement_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict_
     out[k] = (v ^ kCompMask) & valid_mask(k, len);
 }
 
+// The same with 256-bit accesses: thread t produces output words 4t..4t+3 from the 5 input words W-1-4t .. W-5-4t, which
+// always lie in exactly two ALIGNED input vectors (A = the one holding word W-1-4t, B = the one below it); which lanes of
+// A and B are needed depends only on (W-1) % 4, so the selection is uniform over the grid.  A warp reads 1 KiB + one
+// neighbouring vector (B of lane l is A of lane l+1: an L1 hit) and writes 1 KiB.  Threads that would touch the ragged top
+// word, the bottom of the array, or memory past `nwords` fall back to the word-at-a-time formulation.  `in` and `out`
+// 32-byte aligned.
+__global__ void __launch_bounds__(256)
+reverse_complement_vec_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, size_t nwords, size_t len)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t k0 = 4 * t;
+    if (k0 >= nwords) return;
+    const unsigned shift = (unsigned)(2 * ((nwords << 5) - len));           // 0..62 bits
+    const size_t base = nwords - 1 - k0;                                    // highest input word this thread needs
+    const size_t vb = base >> 2;
+    if (t > 0 && k0 + 4 <= nwords && vb >= 1 && 4 * vb + 3 < nwords) {
+        const u64x4 A = ld_stream_u64x4(in + 4 * vb), B = ld_stream_u64x4(in + 4 * (vb - 1));
+        uint64_t c[5];
+        switch (base & 3) {
+        case 3:  c[0] = A.v[3]; c[1] = A.v[2]; c[2] = A.v[1]; c[3] = A.v[0]; c[4] = B.v[3]; break;
+        case 2:  c[0] = A.v[2]; c[1] = A.v[1]; c[2] = A.v[0]; c[3] = B.v[3]; c[4] = B.v[2]; break;
+        case 1:  c[0] = A.v[1]; c[1] = A.v[0]; c[2] = B.v[3]; c[3] = B.v[2]; c[4] = B.v[1]; break;
+        default: c[0] = A.v[0]; c[1] = B.v[3]; c[2] = B.v[2]; c[3] = B.v[1]; c[4] = B.v[0]; break;
+        }
+        if (base < 4) c[4] = 0;                                             // word W-5-4t does not exist: FR beyond the array is 0
+        uint64_t fr[5];
+#pragma unroll
+        for (int i = 0; i < 5; i++) fr[i] = reverse_fields(c[i]);
+        u64x4 o;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint64_t v = fr[i];
+            if (shift) v = (fr[i] >> shift) | (fr[i + 1] << (64 - shift));
+            o.v[i] = (v ^ kCompMask) & valid_mask(k0 + i, len);
+        }
+        st_stream_u64x4(out + k0, o);
+        return;
+    }
+    for (size_t k = k0; k < k0 + 4 && k < nwords; k++) {
+        uint64_t first = in[nwords - 1 - k];
+        if (k == 0) first &= valid_mask(nwords - 1, len);
+        const uint64_t lo = reverse_fields(first);
+        uint64_t v = lo;
+        if (shift) {
+            const uint64_t hi = k + 1 < nwords ? reverse_fields(in[nwords - 2 - k]) : 0ull;
+            v = (lo >> shift) | (hi << (64 - shift));
+        }
+        out[k] = (v ^ kCompMask) & valid_mask(k, len);
+    }
+}
+
 }  // namespace cn
 
 namespace {
@@ -165,9 +216,15 @@ int complement_device(const void *d_in, size_t nwords, size_t len, void *d_out, 
     uint64_t *out = static_cast<uint64_t *>(d_out);
     if (reverse) {
         if (d_in == d_out) return fail(CN_ERR_ARG, "cn_reverse_complement_device: cannot run in place");
-        const size_t blocks = (used + 255) / 256;
-        if (blocks > 0x7FFFFFFFull) return fail(CN_ERR_ARG, "cn_reverse_complement_device: input too large for one launch");
-        cn::reverse_complement_kernel<<<(unsigned)blocks, 256, 0, s>>>(in, out, used, len);
+        if (((addr(d_in) | addr(d_out)) & 31) == 0) {
+            const size_t blocks = ((used + 3) / 4 + 255) / 256;
+            if (blocks > 0x7FFFFFFFull) return fail(CN_ERR_ARG, "cn_reverse_complement_device: input too large for one launch");
+            cn::reverse_complement_vec_kernel<<<(unsigned)blocks, 256, 0, s>>>(in, out, used, len);
+        } else {
+            const size_t blocks = (used + 255) / 256;
+            if (blocks > 0x7FFFFFFFull) return fail(CN_ERR_ARG, "cn_reverse_complement_device: input too large for one launch");
+            cn::reverse_complement_kernel<<<(unsigned)blocks, 256, 0, s>>>(in, out, used, len);
+        }
     } else {
         const size_t nvec = ((addr(d_in) | addr(d_out)) & 31) == 0 ? used / 4 : 0;
         size_t blocks = (nvec + 255) / 256;

@@ -134,14 +134,16 @@ def gather_packed(local_words, total_len: int, root: int = 0, group=None, granul
         raise ValueError(f"rank {rank}: expected {spans[rank][1] - spans[rank][0]} words, got {local_words.numel()}")
     if rank != root:
         if local_words.numel():
-            dist.send(local_words.contiguous(), dst=root, group=group)
+            for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, local_words.contiguous(), root, group)]):
+                q.wait()
         return None
     full = torch.empty(words_for_len(total_len, codec_group), dtype=local_words.dtype, device=local_words.device)
     s, e = spans[root]
     full[s:e] = local_words
-    reqs = [dist.irecv(full[s:e], src=r, group=group) for r, (s, e) in enumerate(spans) if r != root and e > s]
-    for q in reqs:
-        q.wait()
+    ops = [dist.P2POp(dist.irecv, full[s:e], r, group) for r, (s, e) in enumerate(spans) if r != root and e > s]
+    if ops:                                              # one batched (grouped) NCCL call: the receives run concurrently
+        for q in dist.batch_isend_irecv(ops):
+            q.wait()
     return full
 
 
@@ -156,7 +158,8 @@ def scatter_packed(full_words, total_len: int, root: int = 0, group=None, granul
     spans = [word_bounds(total_len, world, r, granule, codec_group) for r in range(world)]
     s, e = spans[rank]
     if rank == root:
-        reqs = [dist.isend(full_words[a:b].contiguous(), dst=r, group=group) for r, (a, b) in enumerate(spans) if r != root and b > a]
+        ops = [dist.P2POp(dist.isend, full_words[a:b], r, group) for r, (a, b) in enumerate(spans) if r != root and b > a]
+        reqs = dist.batch_isend_irecv(ops) if ops else []
         mine = full_words[s:e].clone()
         for q in reqs:
             q.wait()
@@ -164,7 +167,8 @@ def scatter_packed(full_words, total_len: int, root: int = 0, group=None, granul
     ref = like if like is not None else full_words
     mine = torch.empty(e - s, dtype=ref.dtype, device=ref.device)
     if e > s:
-        dist.recv(mine, src=root, group=group)
+        for q in dist.batch_isend_irecv([dist.P2POp(dist.irecv, mine, root, group)]):
+            q.wait()
     return mine
 
 

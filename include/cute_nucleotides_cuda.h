@@ -97,6 +97,10 @@ CN_API int cn_decode_device(const void *d_bits, size_t nwords, size_t len, void 
  * and peer buffers mapped with cn_ipc_open.  Each d_outs[k] is a device pointer ALREADY offset to this shard's first
  * word.  d_n must be 32-byte aligned.  Replaces cn_encode_device + an all-gather of the packed shards. */
 CN_API int cn_encode_multi_device(const void *d_n, size_t len, void *const *d_outs, int nout, void *stream);
+/* The same for the base-5 codec (cn_encode2_device + all-gather / gather-to-root in one kernel): d_n 16-byte aligned,
+ * every d_outs[k] 32-byte aligned and already offset to this shard's first word (shard starts that are multiples of
+ * 108 nucleotides = 4 words keep it so). */
+CN_API int cn_encode2_multi_device(const void *d_n, size_t len, void *const *d_outs, int nout, void *stream);
 /* CUDA IPC plumbing for the above: export a device pointer as a 64-byte handle + offset inside its allocation
  * (send them to the peer process), map it there, unmap it. */
 CN_API int cn_ipc_export(void *d_ptr, void *handle64, size_t *offset);
@@ -130,7 +134,9 @@ CN_API int cn_encode2_ex_device(const void *d_n, size_t len, void *d_out, int mo
 /* Devices the HOST-SLICE calls fan out over.  With count >= 2, one cn_n_to_bits_host / cn_bits_to_n_host (and _ex_, base-5)
  * call is cut by sequence offset into word-aligned ranges (word w depends only on nucleotides 32w..32w+31,
  * src/n_to_bits.rs:39-42) and every range runs on its own GPU -- count PCIe links instead of one -- driven by a worker
- * thread per device inside the library; the result is identical.  count == 0 restores the single-device behaviour
+ * thread per device inside the library; the result is identical.  (Calls on PAGEABLE buffers are bounded by the CPU
+ * staging copies, not by the links, and use at most CN_FANOUT_PAGEABLE_MAX = 2 of the devices.)  count == 0 restores the
+ * single-device behaviour
  * (the device chosen with cn_init, else the current one).  Environment: CN_DEVICES=all or CN_DEVICES=0,1,2 does the same
  * for an unmodified caller. */
 CN_API int cn_set_devices(const int *devices, int count);

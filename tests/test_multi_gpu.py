@@ -159,3 +159,41 @@ def test_gather_to_root_and_scatter_decode_over_peer_memory(cn, oracle, torch_cu
             cn.scatter_decode_from_root(full, bounds, outs)
             cn.synchronize_devices(devices)
             assert b"".join(t.cpu().numpy().tobytes() for t in outs) == oracle.canonical(whole), (total, root)
+
+
+def test_multi_destination_encode_both_codecs(cn, oracle, torch_cuda):
+    """cn_encode_multi_device / cn_encode2_multi_device: the shard is read once and every packed word is stored to each
+    destination.  Destinations live on every visible GPU (peer access) -- or all on device 0 when only one is visible."""
+    import ctypes
+    torch = torch_cuda
+    from cute_nucleotides_b200 import _lib
+    lib = _lib.load()
+    ngpu = torch.cuda.device_count()
+    devices = list(range(min(ngpu, 8)))
+    if ngpu > 1:
+        cn.enable_peer_access(devices)
+    dest_devs = devices if ngpu > 1 else [0, 0, 0]
+    st = torch.cuda.current_stream().cuda_stream
+    for size in (100, 3456 * 5 + 13, (1 << 22) + 77):
+        # 2-bit
+        n = oracle.generate(size, seed=size, alphabet=10)
+        d_n = torch.from_numpy(n).cuda()
+        outs = [torch.full((cn.words_for_len(size) + 4,), -1, dtype=torch.int64, device=f"cuda:{d}") for d in dest_devs]
+        ptrs = (ctypes.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+        _lib.check(lib.cn_encode_multi_device(d_n.data_ptr(), size, ptrs, len(outs), st))
+        cn.synchronize_devices(devices)
+        ref = oracle.n_to_bits(n, "lut")
+        for o in outs:
+            assert np.array_equal(o[:-4].cpu().numpy().view(np.uint64), ref) and int(o[-1].item()) == -1
+        # base-5
+        m = oracle.generate2(size, seed=size + 1, alphabet=12)
+        d_m = torch.from_numpy(m).cuda()
+        outs = [torch.full((cn.words2_for_len(size) + 4,), -1, dtype=torch.int64, device=f"cuda:{d}") for d in dest_devs]
+        ptrs = (ctypes.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+        _lib.check(lib.cn_encode2_multi_device(d_m.data_ptr(), size, ptrs, len(outs), st))
+        cn.synchronize_devices(devices)
+        ref2 = oracle.n_to_bits2(m, "lut")
+        for o in outs:
+            assert np.array_equal(o[:-4].cpu().numpy().view(np.uint64), ref2) and int(o[-1].item()) == -1
+    bad = (ctypes.c_void_p * 1)(outs[0].data_ptr() + 8)
+    assert lib.cn_encode2_multi_device(d_m.data_ptr(), 100, bad, 1, st) == _lib.CN_ERR_ARG      # destination not 32-byte aligned

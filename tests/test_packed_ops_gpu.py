@@ -9,7 +9,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-SIZES = [0, 1, 2, 31, 32, 33, 63, 64, 65, 127, 128, 129, 1000, 4095, 4096, 4097, 40000, (1 << 20) + 17, 3 * (1 << 20) + 5]
+SIZES = [0, 1, 2, 31, 32, 33, 63, 64, 65, 127, 128, 129, 160, 161, 255, 256, 257, 1000, 4095, 4096, 4097, 32 * 1026, 32 * 1027 - 5,
+         32 * 1031 - 1, 32 * 1029, 40000, (1 << 20) + 17, 3 * (1 << 20) + 5]
 
 
 @pytest.fixture(scope="module")

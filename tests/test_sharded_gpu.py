@@ -144,6 +144,7 @@ def _fused_worker(rank, world, port, total, granule, result_dir):
         ok = ok and remote.cpu().numpy().tobytes() == orc.canonical(whole[start:end])
         # encode + gather-to-ROOT only: every rank stores its words into the root's buffer and nowhere else
         root = world - 1
+        dist.barrier()                                       # peers may still be reading this rank's buffer (decode_from above)
         asm.full.fill_(-1)
         torch.cuda.synchronize()
         dist.barrier()
