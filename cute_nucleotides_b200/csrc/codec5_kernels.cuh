@@ -78,6 +78,9 @@ __device__ __forceinline__ uint32_t b5_digits4(uint32_t x)
     return __byte_perm(0x01000000u, 0x03040202u, sel);      // idx: 0,1(A),2 -> 0; 3(C) -> 1; 4(T),5(U) -> 2; 6(N) -> 4; 7(G) -> 3
 }
 
+// one byte -> its digit (the same low-3-bit LUT, scalar form)
+__device__ __forceinline__ uint32_t b5_digit(uint32_t byte) { return (uint32_t)(0x0304020201000000ull >> (8 * (byte & 7))) & 7u; }
+
 // ---- validation fused into the base-5 encode (optional) ----------------------------------------------------
 // A byte belongs to {A,C,G,T,U,N,a,c,g,t,u,n} iff b & 0xD8 equals what its low 3 bits predict: a/c/g (1,3,7) -> 0x40,
 // t/u (4,5) -> 0x50, n (6) -> 0x48; indices 0 and 2 can never match.  The lookup reuses the PRMT selector b5_digits4
@@ -107,15 +110,33 @@ __device__ __forceinline__ uint32_t b5_digits4_mode(uint32_t x, uint32_t &flag)
     flag |= (x & 0xD8D8D8D8u) ^ prmt(0x40FF40FFu, 0x40485050u, sel);
     return __byte_perm(0x01000000u, 0x03040202u, sel);
 }
-// slow path of a lane whose flag fired: exact count, and (kEncLutExact) digit 0 for every byte outside the alphabet,
-// which is what BYTE_LUT of n_to_bits2_lut yields (src/n_to_bits2.rs:8-23)
+// Slow path of a lane whose flag fired: its four words are recomputed byte by byte from the staged tile (exact count; in
+// kEncLutExact every byte outside the alphabet becomes digit 0, which is what BYTE_LUT of n_to_bits2_lut yields,
+// src/n_to_bits2.rs:8-23).  Deliberately rolled loops: this path is rare, and its register footprint must not set the
+// kernel's (the speculative fast path around it runs at the plain kernel's 30 registers).
 template <int MODE>
-__device__ __forceinline__ uint32_t b5_fix_digits4(uint32_t x, uint32_t d, uint32_t &n_invalid)
+__device__ __noinline__ uint32_t b5_recompute_lane(const uint8_t *__restrict__ bytes, uint2 (&w)[4])
 {
-    const uint32_t bad = b5_invalid_bytes_mask(x);
-    n_invalid += __popc(bad);
-    if constexpr (MODE == kEncLutExact) d &= ~((bad >> 7) * 0xFFu);
-    return d;
+    uint32_t invalid = 0;
+#pragma unroll 1
+    for (int g = 0; g < 4; g++) {
+        uint64_t word = 0;
+#pragma unroll 1
+        for (int t = 0; t < 9; t++) {
+            uint32_t e = 0, mul = 1;
+#pragma unroll 1
+            for (int j = 0; j < 3; j++) {
+                const uint32_t byte = bytes[27 * g + 3 * t + j];
+                uint32_t dgt = b5_digit(byte);
+                if (b5_invalid_byte(byte)) { invalid++; if (MODE == kEncLutExact) dgt = 0; }
+                e += dgt * mul;
+                mul *= 5;
+            }
+            word |= (uint64_t)e << (7 * t);
+        }
+        w[g] = make_uint2((uint32_t)word, (uint32_t)(word >> 32));
+    }
+    return invalid;
 }
 
 // 108 digits (the bytes of d[0..26]) -> four packed words.  Triplet j sits at bytes 3j..3j+2; the pattern repeats
@@ -181,7 +202,6 @@ __device__ __forceinline__ void b5_splice108(const uint32_t (&a)[4][7], uint32_t
 }
 
 // ---- scalar paths for whatever the warp tiles do not cover (ragged end, unaligned buffers) -------------
-__device__ __forceinline__ uint32_t b5_digit(uint32_t byte) { return (uint32_t)(0x0304020201000000ull >> (8 * (byte & 7))) & 7u; }
 
 // words [first, total): bytes past len count as digit 0 (src/n_to_bits2.rs:59-70).  Returns the number of bytes outside
 // the alphabet among those this thread read (MODE != kEncPlain).
@@ -277,16 +297,22 @@ b5_encode_kernel(const uint8_t *__restrict__ in, uint64_t *__restrict__ out, siz
         }
         const uint32_t *tw = reinterpret_cast<const uint32_t *>(tile) + 27 * lane;     // this lane's 108 bytes
         uint32_t d[27], flag = 0;
+        if constexpr (MODE == kEncPlain) {
 #pragma unroll
-        for (int k = 0; k < 27; k++) d[k] = b5_digits4_mode<MODE>(tw[k], flag);
-        if constexpr (MODE != kEncPlain) {
-            if (flag) {                                          // rare: something in this lane's 108 bytes is off-alphabet
+            for (int k = 0; k < 27; k++) d[k] = b5_digits4(tw[k]);
+        } else {
+            // volatile: keeps the 27 tile loads in program order.  Without it ptxas hoists all of them above the validation
+            // chain (with TMA staging nothing else orders them) and the kernel lands at 72-80 registers -- a third of the
+            // occupancy, 26 % slower; in order, the packer consumes the digits as they arrive and 32 registers suffice.
+            const volatile uint32_t *vtw = tw;
 #pragma unroll
-                for (int k = 0; k < 27; k++) d[k] = b5_fix_digits4<MODE>(tw[k], d[k], n_invalid);
-            }
+            for (int k = 0; k < 27; k++) d[k] = b5_digits4_mode<MODE>(vtw[k], flag);
         }
         uint2 w[4];
-        b5_pack108(d, w);
+        b5_pack108(d, w);                                        // speculative: right unless the flag fired
+        if constexpr (MODE != kEncPlain) {
+            if (flag) n_invalid += b5_recompute_lane<MODE>(tile + 108 * lane, w);   // rare: something in these 108 bytes is off-alphabet
+        }
         st_stream32(out + g * kB5WarpWords + 4 * lane, make_uint4(w[0].x, w[0].y, w[1].x, w[1].y),
                     make_uint4(w[2].x, w[2].y, w[3].x, w[3].y));
         if constexpr (MULTI) {
@@ -349,23 +375,19 @@ b5_encode_mis_kernel(const uint8_t *__restrict__ in, unsigned mis, uint64_t *__r
         __syncwarp();
         const uint32_t *tw = reinterpret_cast<const uint32_t *>(tile) + (mis >> 2) + 27 * lane;
         const unsigned shift = (mis & 3u) * 8u;
-        uint32_t d[27], x[27], flag = 0;
+        uint32_t d[27], flag = 0;
         uint32_t prev = tw[0];
 #pragma unroll
         for (int k = 0; k < 27; k++) {
             uint32_t next = tw[k + 1];
-            x[k] = __funnelshift_r(prev, next, shift);
-            d[k] = b5_digits4_mode<MODE>(x[k], flag);
+            d[k] = b5_digits4_mode<MODE>(__funnelshift_r(prev, next, shift), flag);
             prev = next;
-        }
-        if constexpr (MODE != kEncPlain) {
-            if (flag) {
-#pragma unroll
-                for (int k = 0; k < 27; k++) d[k] = b5_fix_digits4<MODE>(x[k], d[k], n_invalid);
-            }
         }
         uint2 w[4];
         b5_pack108(d, w);
+        if constexpr (MODE != kEncPlain) {
+            if (flag) n_invalid += b5_recompute_lane<MODE>(tile + mis + 108 * lane, w);
+        }
         st_stream32(out + g * kB5WarpWords + 4 * lane, make_uint4(w[0].x, w[0].y, w[1].x, w[1].y),
                     make_uint4(w[2].x, w[2].y, w[3].x, w[3].y));
     } else if (g == ntiles) {

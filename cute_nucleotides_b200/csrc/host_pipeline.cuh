@@ -631,14 +631,22 @@ int host_batch_one(bool encode, const void *const *in, const size_t *lens, size_
         post_ranges(sl.out_job, batch_scatter, &ctx[k % kSlots], chunks[k]);
         return CN_OK;
     };
-    for (size_t k = 0; k < nchunks; k++) {
+    // gather(k+1) is posted before chunk k is issued, so the copier pool never waits for the issuing thread
+    auto start_gather = [&](size_t k) -> int {
         Slot &sl = p.slot[k % kSlots];
         if (k >= (size_t)kSlots) {
-            if ((rc = scatter_chunk(k - kSlots)) != CN_OK) { first_error = rc; break; }
+            int r = scatter_chunk(k - kSlots);                        // frees the slot: its previous chunk leaves staging
+            if (r != CN_OK) return r;
             pool.wait(sl.out_job);                                    // the slot's context is about to be rewritten
         }
         ctx[k % kSlots] = BatchCtx{encode, in, out, lens, woff.data(), sl.pin_big, sl.pin_small};
         post_ranges(sl.in_job, batch_gather, &ctx[k % kSlots], chunks[k]);
+        return CN_OK;
+    };
+    if (nchunks && (rc = start_gather(0)) != CN_OK) first_error = rc;
+    for (size_t k = 0; k < nchunks && first_error == CN_OK; k++) {
+        Slot &sl = p.slot[k % kSlots];
+        if (k + 1 < nchunks && (rc = start_gather(k + 1)) != CN_OK) { first_error = rc; break; }
         pool.wait(sl.in_job);
         const size_t words = chunks[k].words, nt = words * 32;
         uint8_t *h_in = encode ? sl.pin_big : sl.pin_small, *h_out = encode ? sl.pin_small : sl.pin_big;

@@ -81,10 +81,10 @@ def _ptr_array(a: np.ndarray):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_void_p))
 
 
-def n_to_bits_batch_cuda(buf, offsets):
+def n_to_bits_batch_cuda(buf, offsets, out=None):
     """Encode many independent sequences in ONE call (cn_n_to_bits_host_batch).  Sequence i is buf[offsets[i]:offsets[i+1]]
     (offsets: count+1 non-decreasing integers).  Returns (words, word_offsets): sequence i's packed words -- exactly what
-    n_to_bits_cuda(sequence i) returns -- are words[word_offsets[i]:word_offsets[i+1]]."""
+    n_to_bits_cuda(sequence i) returns -- are words[word_offsets[i]:word_offsets[i+1]].  `out`: a uint64 array to reuse."""
     src = _as_u8(buf)
     offs = np.ascontiguousarray(offsets, dtype=np.uint64)
     count = offs.size - 1
@@ -92,7 +92,9 @@ def n_to_bits_batch_cuda(buf, offsets):
     wcount = (lens + np.uint64(31)) >> np.uint64(5)
     woffs = np.zeros(count + 1, dtype=np.uint64)
     np.cumsum(wcount, out=woffs[1:])
-    words = np.empty(int(woffs[-1]), dtype=np.uint64)
+    words = np.empty(int(woffs[-1]), dtype=np.uint64) if out is None else out[: int(woffs[-1])]
+    if words.dtype != np.uint64 or words.size != int(woffs[-1]) or not words.flags.c_contiguous:
+        raise ValueError("out must be a contiguous uint64 array with room for every sequence's words")
     in_ptrs = np.uint64(src.ctypes.data) + offs[:-1]
     out_ptrs = np.uint64(words.ctypes.data) + woffs[:-1] * np.uint64(8)
     lens_c = lens.ctypes.data_as(ctypes.POINTER(ctypes.c_size_t))
@@ -100,8 +102,9 @@ def n_to_bits_batch_cuda(buf, offsets):
     return words, woffs
 
 
-def bits_to_n_batch_cuda(words, word_offsets, lengths):
-    """Inverse of n_to_bits_batch_cuda: returns (buf, offsets) with sequence i at buf[offsets[i]:offsets[i+1]]."""
+def bits_to_n_batch_cuda(words, word_offsets, lengths, out=None):
+    """Inverse of n_to_bits_batch_cuda: returns (buf, offsets) with sequence i at buf[offsets[i]:offsets[i+1]].
+    `out`: a uint8 array to reuse."""
     w = np.ascontiguousarray(words, dtype=np.uint64)
     woffs = np.ascontiguousarray(word_offsets, dtype=np.uint64)
     lens = np.ascontiguousarray(lengths, dtype=np.uint64)
@@ -110,7 +113,9 @@ def bits_to_n_batch_cuda(words, word_offsets, lengths):
         raise LengthError(_lib.CN_ERR_LENGTH, _lib.load().cn_length_panic_message().decode())
     offs = np.zeros(count + 1, dtype=np.uint64)
     np.cumsum(lens, out=offs[1:])
-    out = np.empty(int(offs[-1]), dtype=np.uint8)
+    out = np.empty(int(offs[-1]), dtype=np.uint8) if out is None else out[: int(offs[-1])]
+    if out.dtype != np.uint8 or out.size != int(offs[-1]) or not out.flags.c_contiguous:
+        raise ValueError("out must be a contiguous uint8 array with room for every sequence")
     in_ptrs = np.uint64(w.ctypes.data) + woffs[:-1] * np.uint64(8)
     out_ptrs = np.uint64(out.ctypes.data) + offs[:-1]
     lens_c = lens.ctypes.data_as(ctypes.POINTER(ctypes.c_size_t))
