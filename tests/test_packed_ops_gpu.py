@@ -118,3 +118,43 @@ def test_packed_ops_at_scale_properties(cn, oracle, torch_cuda):
     tail = oracle.complement(a[-(win // 32 + 1):].cpu().numpy().view(np.uint64), win + 21, reverse=True)
     assert np.array_equal(rc[: win // 32].cpu().numpy().view(np.uint64), tail[: win // 32])
     del comp, rc, back
+
+
+def test_round2_device_calls_are_cuda_graph_capturable(cn, oracle, torch_cuda):
+    """The round-2 device entry points (_lut-exact encode, base-5 validating encode, Hamming, complement, reverse
+    complement) neither allocate nor synchronise either: captured once, replayed on new data."""
+    torch = torch_cuda
+    size = 40000 + 13
+    W = cn.words_for_len(size)
+    d_n = torch.empty(size, dtype=torch.uint8, device="cuda")
+    d_bits = torch.empty(W, dtype=torch.int64, device="cuda")
+    d_comp = torch.empty(W, dtype=torch.int64, device="cuda")
+    d_rc = torch.empty(W, dtype=torch.int64, device="cuda")
+    d_bits2 = torch.empty(cn.words2_for_len(size), dtype=torch.int64, device="cuda")
+    counters = torch.zeros(3, dtype=torch.int64, device="cuda")
+    d_n.copy_(torch.from_numpy(oracle.generate(size, seed=1, alphabet=10)))
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                                 # warm-up outside capture
+        cn.encode_ex_device(d_n, cn.ENC_LUT_EXACT, out=d_bits)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        cn.encode_ex_device(d_n, cn.ENC_LUT_EXACT, counter=counters[0:1], out=d_bits)
+        cn.encode2_ex_device(d_n, cn.ENC_COUNT, counter=counters[1:2], out=d_bits2)
+        cn.complement_device(d_bits, size, out=d_comp)
+        cn.reverse_complement_device(d_bits, size, out=d_rc)
+        cn.hamming_device(d_bits, d_comp, size, result=counters[2:3])
+    for seed in (2, 3, 4):
+        n = oracle.generate(size, seed=seed, alphabet=10)
+        n[seed * 1000] = ord("N")                                 # off the 2-bit alphabet, on the base-5 one
+        n[seed * 1000 + 1] = ord("-")                             # off both
+        d_n.copy_(torch.from_numpy(n))
+        graph.replay()
+        torch.cuda.synchronize()
+        ref = oracle.n_to_bits(n, "lut")
+        assert np.array_equal(d_bits.cpu().numpy().view(np.uint64), ref)
+        assert np.array_equal(d_bits2.cpu().numpy().view(np.uint64), cn.n_to_bits2_cuda(n))
+        assert np.array_equal(d_comp.cpu().numpy().view(np.uint64), oracle.complement(ref, size))
+        assert np.array_equal(d_rc.cpu().numpy().view(np.uint64), oracle.complement(ref, size, reverse=True))
+    assert counters.tolist() == [6, 3, 3 * size]

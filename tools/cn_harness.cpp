@@ -123,6 +123,45 @@ static void test_base5_round_trip_lengths()
     }
 }
 
+static void test_lut_exact_mode()
+{   // n_to_bits_lut maps every byte outside {ACGTUacgtu} to 0 (BYTE_LUT, src/n_to_bits.rs:8-21); the plain variant follows
+    // the SIMD bodies' (b >> 1) & 3.  'N' = 0x4E -> 3 there, 0 here.
+    const std::string s = "ACGTNNNNacgtnnnn-*.ACGT";
+    uint64_t invalid = 0;
+    auto w = n_to_bits_lut_cuda(reinterpret_cast<const uint8_t *>(s.data()), s.size(), &invalid);
+    ASSERT_EQ(invalid, (uint64_t)11);
+    std::string clean = s;
+    for (auto &c : clean) if (std::string("ACGTUacgtu").find(c) == std::string::npos) c = 'A';
+    ASSERT_EQ(w, n_to_bits_cuda(clean));
+    ASSERT_EQ(bits_to_n_cuda(w, s.size()), bytes("ACGTAAAAACGTAAAAAAAACGT"));
+}
+
+static void test_batch()
+{   // element i of the batch == the single call on sequence i (the reference's bench loop, benches/bench_n_to_bits.rs:15-19)
+    std::vector<std::string> store;
+    const std::string unit = "GATTACAgattacaUuCcGgAaTt";
+    for (size_t len : {4, 32, 0, 33, 150, 40000, 31, 100003, 1}) store.push_back(repeat(unit, len / unit.size() + 1).substr(0, len));
+    std::vector<std::string_view> views(store.begin(), store.end());
+    auto res = n_to_bits_cuda_batch(views);
+    ASSERT_EQ(res.size(), store.size());
+    for (size_t i = 0; i < store.size(); i++) ASSERT_EQ(res[i], n_to_bits_cuda(store[i]));
+}
+
+static void test_fan_out_is_transparent()
+{   // cn_set_devices: the same call, the same words, however many GPUs carry it (device 0 twice when only one is visible)
+    int count = 0;
+    cn_device_count(&count);
+    std::vector<int> devs;
+    for (int d = 0; d < std::max(count, 2); d++) devs.push_back(d % std::max(count, 1));
+    const std::string s = repeat("ATCGGCTAacgu", (40u << 20) / 12);
+    const auto one = n_to_bits_cuda(s);
+    cute_nucleotides::n_to_bits::set_devices(devs);
+    const auto many = n_to_bits_cuda(s);
+    ASSERT_EQ(bits_to_n_cuda(many, s.size()).size(), s.size());
+    cute_nucleotides::n_to_bits::set_devices({});
+    ASSERT_EQ(one, many);
+}
+
 template <typename F> static double median_seconds(F f, int min_iters, double min_total)
 {
     std::vector<double> t;
@@ -155,6 +194,18 @@ static void bench_group(size_t repeat_count)
     std::fflush(stdout);
 }
 
+static void bench_batch(size_t repeat_count, size_t sequences)
+{
+    const std::string n = repeat("ATCG", repeat_count);
+    std::vector<std::string_view> many(sequences, std::string_view(n));
+    n_to_bits_cuda_batch(many);
+    double t = median_seconds([&] { auto r = n_to_bits_cuda_batch(many); asm volatile("" ::"r"(r.data()) : "memory"); }, 5, 0.5);
+    const double gib = 1024.0 * 1024.0 * 1024.0;
+    std::printf("{\"group\": \"n_to_bits\", \"function\": \"n_to_bits_cuda_batch\", \"sequences\": %zu, \"nucleotides_each\": %zu, "
+                "\"time_us_per_sequence\": %.3f, \"thrpt_gib_s\": %.4f}\n", sequences, n.size(), t * 1e6 / sequences, n.size() * sequences / t / gib);
+    std::fflush(stdout);
+}
+
 int main(int argc, char **argv)
 {
     const std::string mode = argc > 1 ? argv[1] : "test";
@@ -169,10 +220,14 @@ int main(int argc, char **argv)
             test_n_to_bits2_cuda();
             test_bits_to_n2_cuda();
             test_base5_round_trip_lengths();
-            std::printf(g_failed ? "test result: FAILED. %d failed\n" : "test result: ok. 9 passed; %d failed\n", g_failed);
+            test_lut_exact_mode();
+            test_batch();
+            test_fan_out_is_transparent();
+            std::printf(g_failed ? "test result: FAILED. %d failed\n" : "test result: ok. 12 passed; %d failed\n", g_failed);
             return g_failed ? 1 : 0;
         }
         if (mode == "bench") {
+            bench_batch(10000, 4096);           // 4096 strings of the reference's bench size in ONE call
             bench_group(10000);                 // the reference's bench size: 40 000 nt
             bench_group((1u << 20) / 4);        // 1 MiB
             bench_group((64u << 20) / 4);       // 64 MiB
