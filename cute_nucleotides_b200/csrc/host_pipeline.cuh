@@ -103,16 +103,20 @@ public:
         cv_.notify_all();
     }
 
-    // queue fn(ctx, a, b): an arbitrary piece of staging work (the gather / scatter of a batch of small sequences)
-    void post_fn(Job &job, void (*fn)(void *, size_t, size_t), void *ctx, size_t a, size_t b)
+    // queue fn(ctx, cuts[i], cuts[i+1]) for every i: arbitrary pieces of staging work (the gather / scatter of a batch of
+    // small sequences), posted under one lock with one wake-up
+    void post_fn(Job &job, void (*fn)(void *, size_t, size_t), void *ctx, const std::vector<size_t> &cuts)
     {
+        if (cuts.size() < 2) return;
         ensure_threads();
         {
             std::lock_guard<std::mutex> lk(mu_);
-            queue_.push_back(Task{nullptr, nullptr, 0, &job, fn, ctx, a, b});
-            job.pending++;
+            for (size_t i = 0; i + 1 < cuts.size(); i++) {
+                queue_.push_back(Task{nullptr, nullptr, 0, &job, fn, ctx, cuts[i], cuts[i + 1]});
+                job.pending++;
+            }
         }
-        cv_.notify_one();
+        cv_.notify_all();
     }
 
     // returns when every slice posted on `job` has been copied; the caller copies slices too while it waits
@@ -616,12 +620,16 @@ int host_batch_one(bool encode, const void *const *in, const size_t *lens, size_
     std::vector<BatchCtx> ctx(slots_used ? slots_used : 1);
 
     // gather / scatter of one chunk, cut into pool tasks of >= 128 KiB of payload
+    std::vector<size_t> cuts;
     auto post_ranges = [&](CopyPool::Job &job, void (*fn)(void *, size_t, size_t), BatchCtx *c, const Chunk &ch) {
-        size_t a = ch.i0, acc = 0;
+        cuts.clear();
+        cuts.push_back(ch.i0);
+        size_t acc = 0;
         for (size_t i = ch.i0; i < ch.i1; i++) {
             acc += lens[i];
-            if (acc >= ((size_t)128 << 10) || i + 1 == ch.i1) { pool.post_fn(job, fn, c, a, i + 1); a = i + 1; acc = 0; }
+            if (acc >= ((size_t)128 << 10) || i + 1 == ch.i1) { cuts.push_back(i + 1); acc = 0; }
         }
+        pool.post_fn(job, fn, c, cuts);
     };
     int first_error = CN_OK;
     auto scatter_chunk = [&](size_t k) -> int {                       // wait for chunk k's DMA, start scattering its result
