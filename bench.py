@@ -978,9 +978,10 @@ def main():
     args = ap.parse_args()
 
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
-    if args.gpus != world and world == 1 and args.gpus > 1:
+    if args.impl != "reference" and args.gpus != world and world == 1 and args.gpus > 1:
         raise SystemExit(f"--gpus {args.gpus} needs torchrun: python -m torch.distributed.run --nproc-per-node {args.gpus} bench.py --gpus {args.gpus}")
-    args.gpus = world
+    if args.impl != "reference":
+        args.gpus = world
     if args.impl == "reference":
         run_reference(args, rank)
         return
