@@ -182,7 +182,7 @@ class PeerAssembly:
     waits for the local kernel and then for every rank's (a barrier), after which `self.full` holds the whole
     packed sequence on every rank.  Needs one process per GPU on one NVLink-connected box (world <= 8)."""
 
-    def __init__(self, total_len: int, group=None, granule: int = 1 << 20):
+    def __init__(self, total_len: int, group=None, granule: int = None, codec: str = "2bit"):
         import ctypes
         import torch
         import torch.distributed as dist
@@ -190,11 +190,21 @@ class PeerAssembly:
 
         self._lib, self._ctypes, self._torch, self._dist = _lib, ctypes, torch, dist
         self.lib = _lib.load()
+        self.codec = codec
+        self.grp = GROUP_2BIT if codec == "2bit" else GROUP_BASE5
+        if codec not in ("2bit", "base5"):
+            raise ValueError("codec must be '2bit' or 'base5'")
+        if granule is None:
+            granule = 1 << 20 if codec == "2bit" else BASE5_ALIGNED_GRANULE * 8192
+        if codec == "base5" and granule % BASE5_ALIGNED_GRANULE:
+            raise ValueError("base-5 shards must start on multiples of 108 nucleotides (4 words) so that every destination stays 32-byte aligned")
+        self._enc = self.lib.cn_encode_multi_device if codec == "2bit" else self.lib.cn_encode2_multi_device
+        self._dec = self.lib.cn_decode_device if codec == "2bit" else self.lib.cn_decode2_device
         self.group, self.total_len, self.granule = group, total_len, granule
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if self.world > 8:
             raise ValueError("PeerAssembly supports at most 8 ranks (one NVSwitch domain)")
-        self.full = torch.empty(words_for_len(total_len), dtype=torch.int64, device="cuda")
+        self.full = torch.empty(words_for_len(total_len, self.grp), dtype=torch.int64, device="cuda")
         handle = ctypes.create_string_buffer(64)
         offset = ctypes.c_size_t()
         _lib.check(self.lib.cn_ipc_export(self.full.data_ptr(), handle, ctypes.byref(offset)))
@@ -217,26 +227,25 @@ class PeerAssembly:
         """Launch the fused kernel for this rank's shard (asynchronous).  `dests` = ranks whose buffers receive the packed
         words: all of them by default (encode + all-gather), `[root]` for encode + gather-to-root."""
         torch, ctypes = self._torch, self._ctypes
-        start, end = shard_bounds(self.total_len, self.world, self.rank, self.granule)
+        start, end = shard_bounds(self.total_len, self.world, self.rank, self.granule, self.grp)
         if n_shard.numel() != end - start or n_shard.dtype != torch.uint8 or not n_shard.is_cuda:
             raise ValueError(f"rank {self.rank}: shard must be the uint8 CUDA tensor of nucleotides [{start}, {end})")
-        word_off = (start >> 5) * 8
+        word_off = (start // self.grp) * 8
         ranks = list(range(self.world)) if dests is None else list(dests)
         outs = (ctypes.c_void_p * len(ranks))(*[self.peer_ptrs[r] + word_off for r in ranks])
         s = stream if stream is not None else torch.cuda.current_stream()
-        self._lib.check(self.lib.cn_encode_multi_device(n_shard.data_ptr(), end - start, outs, len(ranks), s.cuda_stream))
+        self._lib.check(self._enc(n_shard.data_ptr(), end - start, outs, len(ranks), s.cuda_stream))
 
     def decode_from(self, source_rank: int, stream=None, out=None):
         """Scatter/broadcast + decode in one kernel: decode THIS rank's range of the packed sequence reading the words
         straight out of `source_rank`'s buffer (peer loads over NVLink) -- no copy of the packed words first."""
         torch = self._torch
-        start, end = shard_bounds(self.total_len, self.world, self.rank, self.granule)
-        ws, we = word_bounds(self.total_len, self.world, self.rank, self.granule)
+        start, end = shard_bounds(self.total_len, self.world, self.rank, self.granule, self.grp)
+        ws, we = word_bounds(self.total_len, self.world, self.rank, self.granule, self.grp)
         if out is None:
             out = torch.empty(end - start, dtype=torch.uint8, device="cuda")
         s = stream if stream is not None else torch.cuda.current_stream()
-        self._lib.check(self.lib.cn_decode_device(self.peer_ptrs[source_rank] + ws * 8, we - ws, end - start,
-                                                  out.data_ptr(), s.cuda_stream))
+        self._lib.check(self._dec(self.peer_ptrs[source_rank] + ws * 8, we - ws, end - start, out.data_ptr(), s.cuda_stream))
         return out
 
     def finish(self):

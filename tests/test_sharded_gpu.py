@@ -158,6 +158,23 @@ def _fused_worker(rank, world, port, total, granule, result_dir):
         torch.cuda.synchronize()
         ok = ok and scattered.cpu().numpy().tobytes() == orc.canonical(whole[start:end])
         asm.close()
+        # the same fused kernels for the base-5 codec (cn_encode2_multi_device; 27-nt words, shards on 108-nt boundaries)
+        total5 = total // 2 + 11
+        g5 = sharded.BASE5_ALIGNED_GRANULE * (64 if total5 > (1 << 20) else 1)
+        s5, e5 = sharded.shard_bounds(total5, world, rank, g5, 27)
+        whole5 = orc.generate2(total5, seed=13, alphabet=12)
+        d5 = torch.from_numpy(whole5[s5:e5]).cuda()
+        asm5 = sharded.PeerAssembly(total5, granule=g5, codec="base5")
+        asm5.full.fill_(-1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        asm5.encode(d5)
+        full5 = asm5.finish()
+        ok = ok and np.array_equal(full5.cpu().numpy().view(np.uint64), orc.n_to_bits2(whole5, "lut"))
+        back5 = asm5.decode_from((rank + 1) % world)
+        torch.cuda.synchronize()
+        ok = ok and back5.cpu().numpy().tobytes() == orc.canonical2(whole5[s5:e5])
+        asm5.close()
         open(os.path.join(result_dir, f"rank{rank}"), "w").write("ok" if ok else "mismatch")
     finally:
         dist.destroy_process_group()
