@@ -41,6 +41,16 @@ int timer_prepare(Timer &t)
     return CN_OK;
 }
 
+// the *_ex_host entry points: validate the mode, zero the counter, run the (possibly fanned-out) host call
+int ex_host(const Codec &cd, const char *who, const uint8_t *n, size_t len, uint64_t *out, int mode, uint64_t *invalid_count)
+{
+    if (mode != CN_ENC_PLAIN && mode != CN_ENC_COUNT && mode != CN_ENC_LUT_EXACT) return fail(CN_ERR_ARG, "%s: bad mode %d", who, mode);
+    if (mode == CN_ENC_COUNT && !invalid_count) return fail(CN_ERR_ARG, "%s: CN_ENC_COUNT needs a counter", who);
+    if (invalid_count) *invalid_count = 0;
+    if (len == 0) return CN_OK;
+    if (!n || !out) return fail(CN_ERR_ARG, "%s: null pointer", who);
+    return host_codec(cd, true, n, reinterpret_cast<uint8_t *>(out), len, HostMode{mode, invalid_count});
+}
 }  // namespace
 
 // ================================================================================================
@@ -116,15 +126,6 @@ int cn_encode_checked_device(const void *d_n, size_t len, void *d_out, void *d_i
     return encode_device(d_n, len, d_out, cn::kEncCount, static_cast<unsigned long long *>(d_invalid_count), static_cast<cudaStream_t>(stream));
 }
 
-static int ex_host(const Codec &cd, const char *who, const uint8_t *n, size_t len, uint64_t *out, int mode, uint64_t *invalid_count)
-{
-    if (mode != CN_ENC_PLAIN && mode != CN_ENC_COUNT && mode != CN_ENC_LUT_EXACT) return fail(CN_ERR_ARG, "%s: bad mode %d", who, mode);
-    if (mode == CN_ENC_COUNT && !invalid_count) return fail(CN_ERR_ARG, "%s: CN_ENC_COUNT needs a counter", who);
-    if (invalid_count) *invalid_count = 0;
-    if (len == 0) return CN_OK;
-    if (!n || !out) return fail(CN_ERR_ARG, "%s: null pointer", who);
-    return host_codec(cd, true, n, reinterpret_cast<uint8_t *>(out), len, HostMode{mode, invalid_count});
-}
 int cn_n_to_bits_ex_host(const uint8_t *n, size_t len, uint64_t *out, int mode, uint64_t *invalid_count)
 {
     return ex_host(kCodec2bit, "cn_n_to_bits_ex_host", n, len, out, mode, invalid_count);

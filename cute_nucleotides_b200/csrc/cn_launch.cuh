@@ -220,7 +220,7 @@ int encode_multi_device(const void *d_n, size_t len, void *const *d_outs, int no
 // base-5 flavour of the above: d_n 16-byte aligned, destinations 32-byte aligned
 int encode2_multi_device(const void *d_n, size_t len, void *const *d_outs, int nout, cudaStream_t s)
 {
-    if (nout < 1 || nout > cn::kMaxPeers + 1 - 1 || !d_outs) return fail(CN_ERR_ARG, "cn_encode2_multi_device: 1..%d destinations", cn::kMaxPeers);
+    if (nout < 1 || nout > cn::kMaxPeers || !d_outs) return fail(CN_ERR_ARG, "cn_encode2_multi_device: 1..%d destinations", cn::kMaxPeers);
     if (len == 0) return CN_OK;
     if (!d_n || (addr(d_n) & 15)) return fail(CN_ERR_ARG, "cn_encode2_multi_device: input must be 16-byte aligned");
     cn::PeerOuts64 more{};

@@ -211,8 +211,7 @@ struct Slot {
     uint8_t *pin_big = nullptr, *pin_small = nullptr;     // ASCII-sized / packed-sized pinned staging
     uint8_t *dev_big = nullptr, *dev_small = nullptr;
     size_t pin_cap = 0, dev_cap = 0;                      // ASCII bytes the staging pairs were sized for
-    CopyPool::Job in_job, out_job;
-    bool in_posted = false, issued = false;
+    CopyPool::Job in_job, out_job;                        // staging copies into / out of this slot that are still running
 };
 
 struct HostPipe {
@@ -428,7 +427,6 @@ int host_codec_one(const Codec &cd, bool encode, const uint8_t *src, uint8_t *ds
         Slot &sl = p.slot[k];
         rc = slot_ensure(sl, stage, staged, !zero_copy);
         if (rc != CN_OK) return rc;
-        sl.in_posted = sl.issued = false;
         if (counted) CN_CUDA(cudaMemsetAsync(p.d_counter + k, 0, sizeof(unsigned long long), sl.stream));
     }
 
@@ -460,12 +458,10 @@ int host_codec_one(const Codec &cd, bool encode, const uint8_t *src, uint8_t *ds
     auto post_in = [&](size_t k) {
         Slot &sl = p.slot[k % kSlots];
         if (!src_pinned) { Geo g = geo(k); pool.post(sl.in_job, pin_in(sl), src + g.in_off, g.in_bytes, g_copy_in_nt); }
-        sl.in_posted = true;
     };
     auto retire = [&](size_t k) -> int {                              // wait for chunk k's DMA, start copying its result out
         Slot &sl = p.slot[k % kSlots];
         cudaError_t e = cudaEventSynchronize(sl.done);
-        sl.issued = false;
         if (e != cudaSuccess) return fail(CN_ERR_CUDA, "host pipeline: chunk %zu failed: %s", k, cudaGetErrorString(e));
         if (!dst_pinned) { Geo g = geo(k); pool.post(sl.out_job, dst + g.out_off, pin_out(sl), g.out_bytes, g_copy_out_nt); }
         return CN_OK;
@@ -512,7 +508,6 @@ int host_codec_one(const Codec &cd, bool encode, const uint8_t *src, uint8_t *ds
         if (e == cudaSuccess && rc == CN_OK) e = cudaEventRecord(sl.done, sl.stream);
         if (e != cudaSuccess) rc = fail(CN_ERR_CUDA, "host pipeline: submitting chunk %zu failed: %s", k, cudaGetErrorString(e));
         if (rc != CN_OK) { first_error = rc; break; }
-        sl.issued = true;
         issued = k + 1;
     }
 
@@ -527,7 +522,7 @@ int host_codec_one(const Codec &cd, bool encode, const uint8_t *src, uint8_t *ds
     }
     for (int k = 0; k < slots_used; k++) {
         Slot &sl = p.slot[k];
-        if (first_error != CN_OK) { cudaStreamSynchronize(sl.stream); sl.issued = false; }
+        if (first_error != CN_OK) cudaStreamSynchronize(sl.stream);
         pool.wait(sl.in_job);
         pool.wait(sl.out_job);
     }

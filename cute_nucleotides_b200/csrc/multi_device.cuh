@@ -193,7 +193,6 @@ int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, s
 
     std::vector<FanJob> jobs(parts);
     FanCall call;
-    size_t live = 0;
     for (size_t k = 0; k < parts; k++) {
         size_t s, e;
         shard_range(len, (int)parts, (int)k, granule, &s, &e);
@@ -204,7 +203,6 @@ int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, s
         const size_t word_off = s / cd.group * 8;
         j.src = src + (encode ? s : word_off);
         j.dst = dst + (encode ? word_off : s);
-        if (j.len) live++;
     }
     // every range but the last goes to its device's worker; the calling thread runs the last one itself
     call.pending = 0;
@@ -218,7 +216,6 @@ int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, s
         call.cv.wait(lk, [&] { return call.pending == 0; });
     }
     if (saved_dev >= 0) { cudaSetDevice(saved_dev); cudaGetLastError(); }
-    (void)live;
     uint64_t invalid = 0;
     for (FanJob &j : jobs) {
         if (j.rc != CN_OK) { snprintf(t_err, sizeof t_err, "%s", j.err); return j.rc; }
