@@ -107,9 +107,12 @@ __device__ __forceinline__ uint32_t b5_digits4_mode(uint32_t x, uint32_t &flag)
     if constexpr (MODE == kEncPlain) return b5_digits4(x);
     uint32_t t = (x & 0x87878787u) | ((x >> 4) & 0x78787878u);            // as in b5_digits4
     uint32_t sel = __byte_perm(t, 0u, 0x4420);
+    // raw PRMT for both lookups: a selector nibble can only have bit 3 set for a byte >= 0x80, which raises the flag and
+    // sends the lane to the exact recompute anyway -- so the & 0x7777 that __byte_perm adds is not needed here
     flag |= (x & 0xD8D8D8D8u) ^ prmt(0x40FF40FFu, 0x40485050u, sel);
-    return __byte_perm(0x01000000u, 0x03040202u, sel);
+    return prmt(0x01000000u, 0x03040202u, sel);
 }
+
 // Slow path of a lane whose flag fired: its four words are recomputed byte by byte from the staged tile (exact count; in
 // kEncLutExact every byte outside the alphabet becomes digit 0, which is what BYTE_LUT of n_to_bits2_lut yields,
 // src/n_to_bits2.rs:8-23).  Deliberately rolled loops: this path is rare, and its register footprint must not set the
