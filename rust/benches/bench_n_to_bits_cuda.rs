@@ -5,7 +5,7 @@
 // reference's (`n_to_bits`, `bits_to_n`) so the results land next to its variants in criterion's reports; inside the
 // reference crate itself the drop-in is the one-liner per group shown in INTEGRATION.md section 4.
 use criterion::{black_box, criterion_group, criterion_main, BenchmarkId, Criterion, Throughput};
-use cute_nucleotides_cuda::{bits_to_n_cuda, n_to_bits_cuda};
+use cute_nucleotides_cuda::{bits_to_n_cuda, n_to_bits_cuda, n_to_bits_cuda_batch};
 
 const SIZES: [usize; 4] = [40_000, 1 << 20, 1 << 26, 1 << 30];
 
@@ -34,5 +34,16 @@ fn codec_benches(c: &mut Criterion) {
     }
 }
 
-criterion_group!(benches, codec_benches);
+// The reference's own bench shape (one 40 000-nucleotide string per call, benches/bench_n_to_bits.rs:10) many at a time:
+// one kernel launch for the whole batch instead of one per string.
+fn batch_bench(c: &mut Criterion) {
+    let one = sequence(40_000);
+    let many: Vec<&[u8]> = (0..4096).map(|_| one.as_slice()).collect();
+    let mut group = c.benchmark_group("n_to_bits");
+    group.throughput(Throughput::Bytes((40_000 * many.len()) as u64));
+    group.bench_function("n_to_bits_cuda_batch", |b| b.iter(|| n_to_bits_cuda_batch(black_box(&many))));
+    group.finish();
+}
+
+criterion_group!(benches, codec_benches, batch_bench);
 criterion_main!(benches);
