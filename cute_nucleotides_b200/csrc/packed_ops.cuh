@@ -196,11 +196,19 @@ int hamming_device(const void *d_a, const void *d_b, size_t nwords, size_t len, 
     if (!d_a || !d_b || ((addr(d_a) | addr(d_b)) & 7)) return fail(CN_ERR_ARG, "cn_hamming_device: null or misaligned pointer");
     const size_t used = cn_words_for_len(len);                       // words beyond ceil(len/32) are never read
     const size_t nvec = ((addr(d_a) | addr(d_b)) & 31) == 0 ? (len >> 5) / 4 : 0;   // whole words only; ragged word -> tail warp
+    static const size_t per_sm = std::getenv("CN_HAMMING_CTAS") ? (size_t)std::atoi(std::getenv("CN_HAMMING_CTAS")) : 4;      // A/B knob
     size_t blocks = (nvec + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > 148 * per_sm) blocks = 148 * per_sm;
     if (blocks == 0) blocks = 1;
-    cn::hamming_kernel<2><<<(unsigned)blocks, 256, 0, s>>>(static_cast<const uint64_t *>(d_a), static_cast<const uint64_t *>(d_b), nvec, used, len,
-                                                          static_cast<unsigned long long *>(d_result));
+    static const int unroll = std::getenv("CN_HAMMING_UNROLL") ? std::atoi(std::getenv("CN_HAMMING_UNROLL")) : 4;   // A/B knob
+    const uint64_t *a = static_cast<const uint64_t *>(d_a), *b = static_cast<const uint64_t *>(d_b);
+    unsigned long long *res = static_cast<unsigned long long *>(d_result);
+    // measured at 2 x 2.5 GiB (tools/bench_packed.py): unroll 1 / 2 / 4 / 8 at 8 CTAs per SM -> 7109 / 7142 / 7365 / 7308 GB/s;
+    // unroll 4 at 2 / 4 / 8 CTAs per SM -> 7341 / 7385 / 7365 (a compute-free pure read tops out at 7547)
+    if (unroll == 1) cn::hamming_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(a, b, nvec, used, len, res);
+    else if (unroll == 4) cn::hamming_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(a, b, nvec, used, len, res);
+    else if (unroll == 8) cn::hamming_kernel<8><<<(unsigned)blocks, 256, 0, s>>>(a, b, nvec, used, len, res);
+    else cn::hamming_kernel<2><<<(unsigned)blocks, 256, 0, s>>>(a, b, nvec, used, len, res);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CN_CUDA(cudaGetLastError());
     return CN_OK;
