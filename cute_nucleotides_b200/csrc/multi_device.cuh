@@ -12,6 +12,7 @@
 #pragma once
 #include "host_pipeline.cuh"
 
+#include <functional>
 #include <map>
 
 namespace {
@@ -87,15 +88,9 @@ struct FanCall {                            // one fanned-out host-slice call
     std::condition_variable cv;
     int pending = 0;
 };
-struct FanJob {
-    const Codec *cd = nullptr;
-    bool encode = false;
-    const uint8_t *src = nullptr;
-    uint8_t *dst = nullptr;
-    size_t len = 0;
-    int enc_mode = cn::kEncPlain;
-    bool counted = false;
-    uint64_t invalid = 0;
+struct FanJob {                             // one device's share of it
+    std::function<int()> work;              // runs on the worker thread with t_device set to the job's device
+    bool live = false;
     int rc = CN_OK;
     char err[sizeof t_err] = "";
     FanCall *call = nullptr;
@@ -105,10 +100,7 @@ int run_fan_job(FanJob &j, int device)
 {
     const int saved = t_device;
     t_device = device;
-    HostMode m;
-    m.enc_mode = j.enc_mode;
-    m.invalid_out = j.counted ? &j.invalid : nullptr;
-    j.rc = host_codec_one(*j.cd, j.encode, j.src, j.dst, j.len, m);
+    j.rc = j.work();
     if (j.rc != CN_OK) { strncpy(j.err, t_err, sizeof j.err - 1); j.err[sizeof j.err - 1] = 0; }
     t_device = saved;
     return j.rc;
@@ -166,6 +158,30 @@ const size_t g_fan_pageable_max = [] {
     return (size_t)(v < 1 ? 1 : v);
 }();
 
+// Job k runs on devs[k]: every job but the last goes to its device's worker, the calling thread runs the last one itself
+// and then waits for the others.  The caller's current device is restored; the first failure is reported.
+int run_fanned_out(std::vector<FanJob> &jobs, const std::vector<int> &devs)
+{
+    int saved_dev = -1;
+    cudaGetDevice(&saved_dev);
+    cudaGetLastError();
+    FanCall call;
+    const size_t parts = jobs.size();
+    for (size_t k = 0; k + 1 < parts; k++)
+        if (jobs[k].live) { jobs[k].call = &call; call.pending++; }
+    for (size_t k = 0; k + 1 < parts; k++)
+        if (jobs[k].live) DeviceWorker::get(devs[k]).submit(&jobs[k]);
+    if (jobs[parts - 1].live) run_fan_job(jobs[parts - 1], devs[parts - 1]);
+    {
+        std::unique_lock<std::mutex> lk(call.mu);
+        call.cv.wait(lk, [&] { return call.pending == 0; });
+    }
+    if (saved_dev >= 0) { cudaSetDevice(saved_dev); cudaGetLastError(); }
+    for (FanJob &j : jobs)
+        if (j.rc != CN_OK) { snprintf(t_err, sizeof t_err, "%s", j.err); return j.rc; }
+    return CN_OK;
+}
+
 // The host-slice entry points land here: one device -> host_codec_one on the calling thread; a device set -> fan out.
 int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, size_t len, const HostMode &mode = HostMode{})
 {
@@ -187,42 +203,59 @@ int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, s
     // ranges are multiples of 1 Mi nucleotides (2-bit) / 256 warp tiles (base-5): whole words, whole chunk units, and
     // 128-byte aligned packed offsets
     const size_t granule = cd.group == 32 ? ((size_t)1 << 20) : (size_t)cn::kB5WarpBytes * 256;
-    int saved_dev = -1;
-    cudaGetDevice(&saved_dev);
-    cudaGetLastError();
 
     std::vector<FanJob> jobs(parts);
-    FanCall call;
+    std::vector<uint64_t> invalid(parts, 0);
+    const bool counted = encode && mode.enc_mode != cn::kEncPlain;
     for (size_t k = 0; k < parts; k++) {
         size_t s, e;
         shard_range(len, (int)parts, (int)k, granule, &s, &e);
-        FanJob &j = jobs[k];
-        j.cd = &cd; j.encode = encode; j.len = e - s; j.enc_mode = mode.enc_mode;
-        j.counted = encode && mode.enc_mode != cn::kEncPlain;
-        j.call = &call;
-        const size_t word_off = s / cd.group * 8;
-        j.src = src + (encode ? s : word_off);
-        j.dst = dst + (encode ? word_off : s);
+        const size_t word_off = s / cd.group * 8, part_len = e - s;
+        const uint8_t *part_src = src + (encode ? s : word_off);
+        uint8_t *part_dst = dst + (encode ? word_off : s);
+        const HostMode part_mode{mode.enc_mode, counted ? &invalid[k] : nullptr};
+        jobs[k].live = part_len != 0;
+        jobs[k].work = [&cd, encode, part_src, part_dst, part_len, part_mode] {
+            return host_codec_one(cd, encode, part_src, part_dst, part_len, part_mode);
+        };
     }
-    // every range but the last goes to its device's worker; the calling thread runs the last one itself
-    call.pending = 0;
-    for (size_t k = 0; k + 1 < parts; k++)
-        if (jobs[k].len) call.pending++;
-    for (size_t k = 0; k + 1 < parts; k++)
-        if (jobs[k].len) DeviceWorker::get(devs[k]).submit(&jobs[k]);
-    if (jobs[parts - 1].len) run_fan_job(jobs[parts - 1], devs[parts - 1]);
-    {
-        std::unique_lock<std::mutex> lk(call.mu);
-        call.cv.wait(lk, [&] { return call.pending == 0; });
-    }
-    if (saved_dev >= 0) { cudaSetDevice(saved_dev); cudaGetLastError(); }
-    uint64_t invalid = 0;
-    for (FanJob &j : jobs) {
-        if (j.rc != CN_OK) { snprintf(t_err, sizeof t_err, "%s", j.err); return j.rc; }
-        invalid += j.invalid;
-    }
-    if (mode.invalid_out) *mode.invalid_out = invalid;
+    int rc = run_fanned_out(jobs, devs);
+    if (rc != CN_OK) return rc;
+    uint64_t total_invalid = 0;
+    for (uint64_t v : invalid) total_invalid += v;
+    if (mode.invalid_out) *mode.invalid_out = total_invalid;
     return CN_OK;
+}
+
+// Batched small sequences: the batch is cut into runs of consecutive sequences of about equal total length, one run per
+// device (the sequences are pageable host memory as a rule, so at most CN_FANOUT_PAGEABLE_MAX devices are used).
+int host_batch(bool encode, const void *const *in, const size_t *lens, size_t count, void *const *out)
+{
+    const std::vector<int> devs = devices_snapshot();
+    size_t total = 0;
+    for (size_t i = 0; i < count; i++) total += lens[i];
+    size_t parts = total / kFanMinPerDevice;
+    if (parts > devs.size()) parts = devs.size();
+    if (parts > g_fan_pageable_max) parts = g_fan_pageable_max;
+    if (devs.empty() || parts <= 1) {
+        if (devs.empty()) return host_batch_one(encode, in, lens, count, out);
+        std::vector<FanJob> one(1);
+        one[0].live = true;
+        one[0].work = [=] { return host_batch_one(encode, in, lens, count, out); };
+        return run_fanned_out(one, devs);
+    }
+    std::vector<FanJob> jobs(parts);
+    size_t first = 0, acc = 0;
+    for (size_t k = 0; k < parts; k++) {
+        const size_t target = total / parts * (k + 1);
+        size_t last = first;
+        while (last < count && (k + 1 == parts || acc + lens[last] <= target)) acc += lens[last++];
+        const size_t n = last - first, at = first;
+        jobs[k].live = n != 0;
+        jobs[k].work = [=] { return host_batch_one(encode, in + at, lens + at, n, out + at); };
+        first = last;
+    }
+    return run_fanned_out(jobs, devs);
 }
 
 // ---- device-resident shards, one per device, single process ---------------------------------------------

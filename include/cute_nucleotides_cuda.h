@@ -80,7 +80,8 @@ CN_API int cn_bits_to_n_host(const uint64_t *bits, size_t nwords, size_t len, ui
  * 38-39) is launch-latency-bound on a GPU one call at a time; here sequence i -- seqs[i][0 .. lens[i]) -- is encoded into
  * outs[i][0 .. cn_words_for_len(lens[i])) exactly as cn_n_to_bits_host would, but thousands of sequences share one kernel
  * launch and one pair of PCIe transfers.  The inverse decodes lens[i] nucleotides from bits[i] (which must hold
- * cn_words_for_len(lens[i]) words) into outs[i].  Zero-length sequences are skipped (their pointers may be NULL). */
+ * cn_words_for_len(lens[i]) words) into outs[i].  Zero-length sequences are skipped (their pointers may be NULL).  With a
+ * device set (cn_set_devices) the batch is cut into runs of consecutive sequences, one run per device. */
 CN_API int cn_n_to_bits_host_batch(const uint8_t *const *seqs, const size_t *lens, size_t count, uint64_t *const *outs);
 CN_API int cn_bits_to_n_host_batch(const uint64_t *const *bits, const size_t *lens, size_t count, uint8_t *const *outs);
 

@@ -73,6 +73,21 @@ def test_batch_with_sequences_larger_than_a_chunk(cn, oracle):
     check_batch(cn, oracle, [100, 100000, 5, 70000, 65536, 65537, 31, 200001, 77], 6)
 
 
+def test_batch_fans_out_over_the_device_set(cn, oracle):
+    """With cn_set_devices the batch is cut into runs of consecutive sequences, one per device (device 0 twice when only
+    one GPU is visible: a worker thread plus the caller)."""
+    import torch
+    devs = list(range(torch.cuda.device_count())) if torch.cuda.device_count() > 1 else [0, 0]
+    cn.set_devices(devs)
+    try:
+        rng = np.random.default_rng(11)
+        check_batch(cn, oracle, rng.integers(100, 2000, size=40000), 8)          # ~42 M nt: split in two
+        check_batch(cn, oracle, [40000] * 1000, 9)
+        check_batch(cn, oracle, [5, 0, 77], 10)                                   # too small to split: runs on devs[0]
+    finally:
+        cn.set_devices([])
+
+
 def test_batch_from_threads(cn, oracle):
     import threading
     errors = []
