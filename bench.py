@@ -526,6 +526,28 @@ def run_extras(cn, torch, d_n, d_bits, d_out, L, iters=20):
         batch[name] = {"sequences": int(offs.size - 1), "nucleotides": total, "encode_nt_per_s": total / t_en, "roundtrip_nt_per_s": total / t_rt,
                        "us_per_sequence_encode": t_en / (offs.size - 1) * 1e6,
                        "matches_single_call": bool(np.array_equal(words[int(woffs[i]): int(woffs[i + 1])], one))}
+    # the same two shapes RESIDENT IN HBM, tightly concatenated (cn_encode_segmented_device / cn_decode_segmented_device):
+    # algorithmic traffic ~1.25 B/nt + 16 B of offsets per sequence per direction
+    seg = {}
+    for name, (lo, hi, n_seq) in {"40000nt_x25000": (40000, 40001, 25000), "reads_150_300nt_x4000000": (150, 301, 4000000)}.items():
+        lens_t = torch.randint(lo, hi, (n_seq,), device=dev, dtype=torch.int64, generator=torch.Generator(device=dev).manual_seed(SEED))
+        offs_t = torch.zeros(n_seq + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(lens_t, dim=0, out=offs_t[1:])
+        total = int(offs_t[-1].item())
+        d_seq = cn.generate_device(d_n[:total], 0, SEED, 10)
+        woffs_t = cn.segment_word_offsets(offs_t)
+        d_w = d_bits[: int(woffs_t[-1].item())]
+        ms_e = timed(lambda: cn.encode_segmented_device(d_seq, offs_t, woffs_t, out=d_w))
+        ms_d = timed(lambda: cn.decode_segmented_device(d_w, offs_t, woffs_t, out=d_out[:total]))
+        i = n_seq // 2
+        s_, e_ = int(offs_t[i].item()), int(offs_t[i + 1].item())
+        one = cn.encode_device(d_seq[s_:e_].clone())
+        ok = bool(torch.equal(d_w[int(woffs_t[i].item()): int(woffs_t[i + 1].item())], one))
+        seg[name] = {"sequences": n_seq, "nucleotides": total, "encode_ms": ms_e, "decode_ms": ms_d,
+                     "encode_nt_per_s": total / (ms_e * 1e-3), "decode_nt_per_s": total / (ms_d * 1e-3),
+                     "encode_gbs": gbs(1.25 * total + 16 * n_seq, ms_e), "decode_gbs": gbs(1.25 * total + 16 * n_seq, ms_d),
+                     "matches_single_call": ok}
+    out["segmented_device"] = seg
     a = time.perf_counter()
     for _ in range(200):
         cn.n_to_bits_cuda(buf[:40000])

@@ -32,6 +32,8 @@ PROTOTYPES = {
     "cn_bits_to_n_host_batch": (c_int, [POINTER(c_void_p), POINTER(c_size_t), c_size_t, POINTER(c_void_p)]),
     "cn_encode_device": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "cn_decode_device": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
+    "cn_encode_segmented_device": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p]),
+    "cn_decode_segmented_device": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p]),
     "cn_encode_multi_device": (c_int, [c_void_p, c_size_t, POINTER(c_void_p), c_int, c_void_p]),
     "cn_encode2_multi_device": (c_int, [c_void_p, c_size_t, POINTER(c_void_p), c_int, c_void_p]),
     "cn_ipc_export": (c_int, [c_void_p, c_void_p, POINTER(c_size_t)]),

@@ -170,6 +170,17 @@ int cn_decode_sharded(int nshards, const int *devices, const void *const *d_bits
 int cn_enable_peer_access(const int *devices, int count) { return enable_peer_access(devices, count); }
 int cn_synchronize_devices(const int *devices, int count) { return synchronize_devices(devices, count); }
 
+int cn_encode_segmented_device(const void *d_n, const void *d_offsets, const void *d_word_offsets, size_t count, size_t total_len,
+                               size_t total_words, void *d_out, void *stream)
+{
+    return segmented_device(true, d_n, d_offsets, d_word_offsets, count, total_len, total_words, d_out, static_cast<cudaStream_t>(stream));
+}
+int cn_decode_segmented_device(const void *d_bits, const void *d_offsets, const void *d_word_offsets, size_t count, size_t total_len,
+                               size_t total_words, void *d_out, void *stream)
+{
+    return segmented_device(false, d_bits, d_offsets, d_word_offsets, count, total_len, total_words, d_out, static_cast<cudaStream_t>(stream));
+}
+
 int cn_encode_multi_device(const void *d_n, size_t len, void *const *d_outs, int nout, void *stream)
 {
     return encode_multi_device(d_n, len, d_outs, nout, static_cast<cudaStream_t>(stream));

@@ -4,6 +4,7 @@
 #include "cn_common.cuh"
 #include "codec_kernels.cuh"
 #include "codec5_kernels.cuh"
+#include "segmented_kernels.cuh"
 
 namespace {
 
@@ -403,6 +404,31 @@ int decode2_device(const void *d_bits, size_t nwords, size_t len, void *d_out, c
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(CN_ERR_CUDA, "base-5 decode kernel launch failed: %s", cudaGetErrorString(e));
+    return CN_OK;
+}
+
+// ---- many sequences resident in HBM, tightly concatenated (segmented_kernels.cuh) ----------------------------------
+int segmented_device(bool encode, const void *d_src, const void *d_offsets, const void *d_word_offsets, size_t count,
+                     size_t total_len, size_t total_words, void *d_dst, cudaStream_t s)
+{
+    const char *who = encode ? "cn_encode_segmented_device" : "cn_decode_segmented_device";
+    if (count == 0 || total_words == 0) return CN_OK;
+    if (!d_src || !d_dst || !d_offsets || !d_word_offsets) return fail(CN_ERR_ARG, "%s: null pointer", who);
+    if ((addr(d_offsets) | addr(d_word_offsets)) & 7) return fail(CN_ERR_ARG, "%s: offset arrays must be 8-byte aligned", who);
+    if (addr(encode ? d_dst : d_src) & 7) return fail(CN_ERR_ARG, "%s: packed words must be 8-byte aligned", who);
+    if (total_len > total_words * 32 || total_words > total_len + count) return fail(CN_ERR_LENGTH, "%s", kPanicText);
+    const size_t blocks = (total_words + cn::kSegWords - 1) / cn::kSegWords;
+    if (blocks > kMaxGrid) return fail(CN_ERR_ARG, "%s: too many words for one launch", who);
+    const uint64_t *off = static_cast<const uint64_t *>(d_offsets), *woff = static_cast<const uint64_t *>(d_word_offsets);
+    if (encode)
+        cn::encode_segmented_kernel<<<(unsigned)blocks, cn::kSegThreads, 0, s>>>(static_cast<const uint8_t *>(d_src), off, woff, count,
+                                                                                total_words, total_len, static_cast<uint64_t *>(d_dst));
+    else
+        cn::decode_segmented_kernel<<<(unsigned)blocks, cn::kSegThreads, 0, s>>>(static_cast<const uint64_t *>(d_src), off, woff, count,
+                                                                                total_words, static_cast<uint8_t *>(d_dst));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(CN_ERR_CUDA, "%s: launch failed: %s", who, cudaGetErrorString(e));
     return CN_OK;
 }
 

@@ -22,6 +22,7 @@ from ._lib import LengthError, check
 __all__ = [
     "n_to_bits_cuda", "bits_to_n_cuda", "words_for_len", "n_to_bits_checked_cuda", "encode_checked_device",
     "n_to_bits_lut_cuda", "n_to_bits_ex_cuda", "encode_ex_device", "n_to_bits_batch_cuda", "bits_to_n_batch_cuda",
+    "encode_segmented_device", "decode_segmented_device", "segment_word_offsets",
     "encode_device", "decode_device", "generate_device", "generate_words_device", "LengthError",
     "ENC_PLAIN", "ENC_COUNT", "ENC_LUT_EXACT",
 ]
@@ -188,6 +189,48 @@ def encode_ex_device(n, mode: int, counter=None, out=None, stream=None):
     with torch.cuda.device(n.device):
         check(_lib.load().cn_encode_ex_device(n.data_ptr(), length, out.data_ptr(), mode,
                                               counter.data_ptr() if counter is not None else None, _stream_ptr(stream)))
+    return out
+
+
+def segment_word_offsets(offsets):
+    """offsets: int64 CUDA (or CPU) tensor of count+1 byte offsets -> word offsets of the padded packed layout
+    (sequence i gets ceil(len_i / 32) words), same device."""
+    import torch
+    lens = offsets[1:] - offsets[:-1]
+    woff = torch.zeros_like(offsets)
+    torch.cumsum((lens + 31) >> 5, dim=0, out=woff[1:])
+    return woff
+
+
+def encode_segmented_device(n, offsets, word_offsets=None, out=None, stream=None):
+    """Many sequences resident in HBM, tightly concatenated in the uint8 CUDA tensor `n`: sequence i = n[offsets[i]:offsets[i+1]]
+    (offsets: int64 CUDA tensor, count+1 entries, offsets[0] == 0, offsets[-1] == n.numel()).  Returns (words, word_offsets):
+    sequence i's packed words -- what n_to_bits_lut(sequence i) yields -- are words[word_offsets[i]:word_offsets[i+1]]."""
+    import torch
+    if n.dtype != torch.uint8 or not n.is_cuda or offsets.dtype != torch.int64 or not offsets.is_cuda:
+        raise TypeError("encode_segmented_device expects a uint8 CUDA tensor and int64 CUDA offsets")
+    if word_offsets is None:
+        word_offsets = segment_word_offsets(offsets)
+    count = offsets.numel() - 1
+    total_words = int(word_offsets[-1].item())
+    if out is None:
+        out = torch.empty(total_words, dtype=torch.int64, device=n.device)
+    with torch.cuda.device(n.device):
+        check(_lib.load().cn_encode_segmented_device(n.data_ptr(), offsets.data_ptr(), word_offsets.data_ptr(), count, n.numel(),
+                                                     total_words, out.data_ptr(), _stream_ptr(stream)))
+    return out, word_offsets
+
+
+def decode_segmented_device(words, offsets, word_offsets, out=None, stream=None):
+    """Inverse of encode_segmented_device: returns the uint8 CUDA tensor of offsets[-1] ASCII bytes."""
+    import torch
+    count = offsets.numel() - 1
+    total_len = int(offsets[-1].item())
+    if out is None:
+        out = torch.empty(total_len, dtype=torch.uint8, device=words.device)
+    with torch.cuda.device(words.device):
+        check(_lib.load().cn_decode_segmented_device(words.data_ptr(), offsets.data_ptr(), word_offsets.data_ptr(), count, total_len,
+                                                     words.numel(), out.data_ptr(), _stream_ptr(stream)))
     return out
 
 

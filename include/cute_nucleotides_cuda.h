@@ -93,6 +93,17 @@ CN_API int cn_encode_device(const void *d_n, size_t len, void *d_out, void *stre
 /* d_bits 8-byte aligned; d_out any alignment (16-byte aligned takes the fast path). */
 CN_API int cn_decode_device(const void *d_bits, size_t nwords, size_t len, void *d_out, void *stream);
 
+/* Many independent sequences that already live in HBM, tightly concatenated: sequence i = bytes [offsets[i], offsets[i+1])
+ * of d_n and words [word_offsets[i], word_offsets[i+1]) of the packed side, word_offsets[i+1] - word_offsets[i] =
+ * cn_words_for_len(len_i) -- per sequence exactly what n_to_bits_lut / bits_to_n_lut produce (src/n_to_bits.rs:34-69).
+ * d_offsets / d_word_offsets: count + 1 non-decreasing uint64 in DEVICE memory, first element 0; total_len =
+ * offsets[count], total_words = word_offsets[count] (the caller knows them; the library does not read device memory back).
+ * One launch, any alignment of d_n / d_out; the device-resident counterpart of the *_host_batch calls. */
+CN_API int cn_encode_segmented_device(const void *d_n, const void *d_offsets, const void *d_word_offsets, size_t count,
+                                      size_t total_len, size_t total_words, void *d_out, void *stream);
+CN_API int cn_decode_segmented_device(const void *d_bits, const void *d_offsets, const void *d_word_offsets, size_t count,
+                                      size_t total_len, size_t total_words, void *d_out, void *stream);
+
 /* ---- multi-GPU: encode + assemble in ONE kernel over NVLink peer memory (one process per GPU) ---------------- */
 /* Reads the shard once and stores every packed word to `nout` (1..8) destinations: the caller's own assembled buffer
  * and peer buffers mapped with cn_ipc_open.  Each d_outs[k] is a device pointer ALREADY offset to this shard's first
