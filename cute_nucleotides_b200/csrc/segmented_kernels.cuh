@@ -119,64 +119,57 @@ __device__ __forceinline__ void seg_locate(const uint64_t *__restrict__ off, con
     __syncthreads();
 }
 
+// Encode needs no tile: a word's (up to) 32 bytes lie inside three ALIGNED 16-byte vectors, which the thread loads
+// straight from global memory (a warp's words are consecutive, so the three loads of a warp cover one contiguous ~1 KiB
+// span; the third vector of a lane is the first of the next: an L1 hit) and aligns in registers -- a select network picks
+// the 9 words that contain the bytes, funnel shifts do the byte alignment.  Only the lookup result goes through shared
+// memory.  (The first version staged the ASCII range in a shared-memory tile like the decoder below still does; ncu showed it
+// issue-bound -- 230 instructions per word, mostly tile address arithmetic -- at 3.3 Tnt/s.)
 __global__ void __launch_bounds__(kSegThreads)
 encode_segmented_kernel(const uint8_t *__restrict__ n, const uint64_t *__restrict__ off, const uint64_t *__restrict__ woff,
                         size_t count, uint64_t total_words, uint64_t total_bytes, uint64_t *__restrict__ out)
 {
-    __shared__ uint32_t tile[kSegTileWords];
     __shared__ SegShared sh;
     const uint64_t w0 = (uint64_t)blockIdx.x * kSegWords;
     seg_locate(off, woff, count, total_words, w0, sh);
-    // aligned vectors covering [lo, hi): addresses are aligned in ADDRESS space, so the buffer's own misalignment counts
-    const uintptr_t a0 = reinterpret_cast<uintptr_t>(n);
-    const uint64_t lo_addr = (a0 + sh.lo) & ~(uint64_t)15, hi_addr = (a0 + sh.hi + 15) & ~(uint64_t)15;
-    const uint32_t nvec = (uint32_t)((hi_addr - lo_addr) >> 4);
-    const bool inside = lo_addr >= a0 && hi_addr <= a0 + total_bytes;              // no vector sticks out of the buffer
-    if (inside) {
-        constexpr int kRounds = (kSegTileBytes / 16 + kSegThreads - 1) / kSegThreads;
-        uint4 val[kRounds];
-#pragma unroll
-        for (int r = 0; r < kRounds; r++) {                                         // all loads first: they are independent
-            const uint32_t v = threadIdx.x + kSegThreads * r;
-            if (v < nvec) val[r] = ld_stream16(reinterpret_cast<const void *>(lo_addr + 16ull * v));
-        }
-#pragma unroll
-        for (int r = 0; r < kRounds; r++) {
-            const uint32_t v = threadIdx.x + kSegThreads * r;
-            if (v < nvec) {
-                tile[seg_slot(4 * v)] = val[r].x; tile[seg_slot(4 * v + 1)] = val[r].y;
-                tile[seg_slot(4 * v + 2)] = val[r].z; tile[seg_slot(4 * v + 3)] = val[r].w;
-            }
-        }
-    } else {
-        for (uint32_t v = threadIdx.x; v < nvec; v += kSegThreads) {               // first / last tile of the buffer: byte-wise edges
-            const uint64_t addr = lo_addr + 16ull * v;
-            uint32_t b4[4] = {0u, 0u, 0u, 0u};
-#pragma unroll 1
-            for (int k = 0; k < 16; k++) {
-                const uint64_t a = addr + k;
-                if (a >= a0 && a < a0 + total_bytes) b4[k >> 2] |= (uint32_t)n[a - a0] << (8 * (k & 3));
-            }
-            for (int q = 0; q < 4; q++) tile[seg_slot(4 * v + q)] = b4[q];
-        }
-    }
-    __syncthreads();
-    const uint32_t tile0 = (uint32_t)(lo_addr - a0);                     // ASCII offset of the tile's first byte (low 32 bits)
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(n), a_end = a0 + total_bytes;
+    const uint64_t hi32 = sh.lo & ~0xFFFFFFFFull;                        // p32 holds the low half; the tile spans < 2^14 bytes
+    const uint32_t lo32 = (uint32_t)sh.lo;
 #pragma unroll
     for (int j = 0; j < kSegWpt; j++) {
         const uint32_t i = threadIdx.x + kSegThreads * j, avail = sh.avail[i];
         if (!avail) continue;
-        // this word's (up to) 32 bytes start `o` bytes into the tile: 9 aligned shared-memory words + a funnel shift
-        const uint32_t o = sh.p32[i] - tile0, base = o >> 2;
-        const unsigned shift = (o & 3u) * 8u;
-        uint32_t x[8];
-        uint32_t prev = tile[seg_slot(base)];
+        const uint32_t p32 = sh.p32[i];
+        const uint64_t addr = a0 + ((hi32 | p32) + (p32 < lo32 ? 0x100000000ull : 0ull));       // of the word's first byte
+        const uint64_t va = addr & ~(uint64_t)15;
+        uint32_t r[12];
+        if (va >= a0 && va + 48 <= a_end) {
+            const uint4 v0 = ld_stream16(reinterpret_cast<const void *>(va));
+            const uint4 v1 = ld_stream16(reinterpret_cast<const void *>(va + 16));
+            const uint4 v2 = __ldg(reinterpret_cast<const uint4 *>(va + 32));
+            r[0] = v0.x; r[1] = v0.y; r[2] = v0.z; r[3] = v0.w; r[4] = v1.x; r[5] = v1.y; r[6] = v1.z; r[7] = v1.w;
+            r[8] = v2.x; r[9] = v2.y; r[10] = v2.z; r[11] = v2.w;
+        } else {                                                          // a vector sticks out of the buffer: take only its bytes
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const uint32_t next = tile[seg_slot(base + k + 1)];          // at most 4 bytes past the word: inside the slack
-            x[k] = __funnelshift_r(prev, next, shift);
-            prev = next;
+            for (int q = 0; q < 12; q++) {                                // (unrolled: r[] must stay in registers)
+                uint32_t v = 0;
+#pragma unroll 1
+                for (int k = 0; k < 4; k++) {
+                    const uint64_t a = va + 4 * q + k;
+                    if (a >= a0 && a < a_end) v |= (uint32_t)n[a - a0] << (8 * k);
+                }
+                r[q] = v;
+            }
         }
+        // the word's bytes start (addr & 15) bytes into r[]: drop (addr & 15) >> 2 whole registers, then shift by the rest
+        const unsigned wsel = (unsigned)(addr & 15) >> 2, shift = (unsigned)(addr & 3) * 8u;
+        uint32_t t[10], u[9], x[8];
+#pragma unroll
+        for (int k = 0; k < 10; k++) t[k] = (wsel & 2u) ? r[k + 2] : r[k];
+#pragma unroll
+        for (int k = 0; k < 9; k++) u[k] = (wsel & 1u) ? t[k + 1] : t[k];
+#pragma unroll
+        for (int k = 0; k < 8; k++) x[k] = __funnelshift_r(u[k], u[k + 1], shift);
         // bytes at and beyond `avail` belong to the next sequence (or to nobody): they encode as 0, like the zeroed word of
         // n_to_bits_lut (src/n_to_bits.rs:35)
         if (avail < 32) {
@@ -186,7 +179,7 @@ encode_segmented_kernel(const uint8_t *__restrict__ n, const uint64_t *__restric
                 x[k] = keep >= 4 ? x[k] : (keep <= 0 ? 0u : (x[k] & ((1u << (8 * keep)) - 1u)));
             }
         }
-        st_stream8(out + w0 + threadIdx.x + kSegThreads * j, pack16(x[0], x[1], x[2], x[3]), pack16(x[4], x[5], x[6], x[7]));
+        st_stream8(out + w0 + i, pack16(x[0], x[1], x[2], x[3]), pack16(x[4], x[5], x[6], x[7]));
     }
 }
 
@@ -221,22 +214,28 @@ decode_segmented_kernel(const uint64_t *__restrict__ bits, const uint64_t *__res
         const uint32_t y[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         const uint32_t o = sh.p32[i] - tile0, base = o >> 2;
         const unsigned s = o & 3u;
-        // shifted image: word k of the tile window holds decoded bytes 4k - s .. 4k - s + 3
-        uint32_t prev = 0;
+        // Shifted image: word k of the tile window holds decoded bytes 4k - s .. 4k - s + 3.  Words [k0, k1) are wholly this
+        // word's (one store each, predicated, no divergence between full and ragged words of a warp); the head word 0 (from
+        // byte s on, when s > 0) and the tail word k1 (its first (avail + s) & 3 bytes) are shared with the neighbours and
+        // written byte by byte.
+        uint32_t *t0 = tile + seg_slot(base);
+        const uint32_t c = 8u - (base & 7u);                              // tile words until the next pad word
+        auto slot_ptr = [&](uint32_t k) { return t0 + k + (k >= c ? 1u : 0u); };
+        const uint32_t k1 = ((uint32_t)avail + s) >> 2, rem = ((uint32_t)avail + s) & 3u;
+        uint32_t tail = 0;
+        if (s == 0 && k1 > 0) *slot_ptr(0) = y[0];
 #pragma unroll
-        for (int k = 0; k < 9; k++) {
-            const uint32_t cur = k < 8 ? y[k] : 0u;
-            const uint32_t v = __funnelshift_l(prev, cur, s * 8u);        // low s bytes from prev's top, the rest from cur
-            const int first = 4 * k - (int)s;                             // decoded-byte index of this tile word's byte 0
-            if (first >= 0 && first + 3 < avail) tile[seg_slot(base + k)] = v;      // all four bytes are this word's: one store
-            else {
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (first + q >= 0 && first + q < avail)
-                        reinterpret_cast<uint8_t *>(tile + seg_slot(base + k))[q] = (uint8_t)(v >> (8 * q));
-            }
-            prev = cur;
+        for (uint32_t k = 1; k < 9; k++) {
+            const uint32_t v = __funnelshift_l(y[k - 1], k < 8 ? y[k] : 0u, s * 8u);
+            if (k < 8 && k < k1) *slot_ptr(k) = v;
+            if (k == k1) tail = v;
         }
+        if (s != 0 || k1 == 0) {                                          // head: bytes s .. 3 of tile word 0 (fewer if avail is tiny)
+            const uint32_t v0 = y[0] << (s * 8u), stop = s + (uint32_t)avail < 4u ? s + (uint32_t)avail : 4u;
+            for (uint32_t q = s; q < stop; q++) reinterpret_cast<uint8_t *>(slot_ptr(0))[q] = (uint8_t)(v0 >> (8 * q));
+        }
+        if (k1 > 0)                                                       // tail: the first `rem` bytes of tile word k1
+            for (uint32_t q = 0; q < rem; q++) reinterpret_cast<uint8_t *>(slot_ptr(k1))[q] = (uint8_t)(tail >> (8 * q));
     }
     __syncthreads();
     const uint32_t nvec = (uint32_t)((hi_addr - lo_addr) >> 4);
