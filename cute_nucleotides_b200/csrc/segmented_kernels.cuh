@@ -93,8 +93,9 @@ __device__ __forceinline__ void seg_locate(const uint64_t *__restrict__ off, con
     __syncthreads();
     const uint32_t i0 = kSegWpt * threadIdx.x;
     if (i0 < nw) {
+        // all words of the CTA in ONE sequence (long sequences: most CTAs): nothing to search
         const float ratio = nw > 1 ? (float)(sh.last - sh.first) / (float)(nw - 1) : 0.f;
-        size_t s = seg_find(woff, count, sh.first + (size_t)(ratio * (float)i0), w0 + i0);
+        size_t s = sh.first == sh.last ? (size_t)sh.first : seg_find(woff, count, sh.first + (size_t)(ratio * (float)i0), w0 + i0);
         uint64_t ws = woff[s], we = woff[s + 1], os = off[s], oe = off[s + 1];
 #pragma unroll
         for (int j = 0; j < kSegWpt; j++) {
