@@ -143,7 +143,9 @@ public:
         return job.pending == 0;
     }
 
-    static constexpr size_t kSlice = (size_t)512 << 10;
+    // small enough that a mid-sized call (1 MiB = two 512 KiB chunks) still spreads over several copiers, large enough that
+    // queue traffic stays negligible (32 tasks per 4 MiB chunk)
+    static constexpr size_t kSlice = (size_t)128 << 10;
 
 private:
     struct Task {
