@@ -143,14 +143,16 @@ int cn_encode2_ex_device(const void *d_n, size_t len, void *d_out, int mode, voi
     return encode2_device(d_n, len, d_out, mode, static_cast<unsigned long long *>(d_invalid_count), static_cast<cudaStream_t>(stream));
 }
 
-int cn_set_devices(const int *devices, int count) { return set_devices(devices, count); }
+int cn_set_devices(const int *devices, int count) { return no_throw([&] { return set_devices(devices, count); }); }
 int cn_get_devices(int *devices, int capacity, int *count)
 {
     if (!count || capacity < 0 || (capacity > 0 && !devices)) return fail(CN_ERR_ARG, "cn_get_devices: bad arguments");
-    const std::vector<int> devs = devices_snapshot();
-    *count = (int)devs.size();
-    for (int i = 0; i < capacity && i < (int)devs.size(); i++) devices[i] = devs[i];
-    return CN_OK;
+    return no_throw([&] {
+        const std::vector<int> devs = devices_snapshot();
+        *count = (int)devs.size();
+        for (int i = 0; i < capacity && i < (int)devs.size(); i++) devices[i] = devs[i];
+        return (int)CN_OK;
+    });
 }
 int cn_shard_bounds(size_t total_len, int nshards, int shard, size_t granule, size_t *start, size_t *end)
 {

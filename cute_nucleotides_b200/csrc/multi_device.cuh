@@ -12,8 +12,10 @@
 #pragma once
 #include "host_pipeline.cuh"
 
+#include <exception>
 #include <functional>
 #include <map>
+#include <new>
 
 namespace {
 
@@ -183,7 +185,7 @@ int run_fanned_out(std::vector<FanJob> &jobs, const std::vector<int> &devs)
 }
 
 // The host-slice entry points land here: one device -> host_codec_one on the calling thread; a device set -> fan out.
-int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, size_t len, const HostMode &mode = HostMode{})
+int host_codec_impl(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, size_t len, const HostMode &mode)
 {
     if (mode.invalid_out) *mode.invalid_out = 0;
     const std::vector<int> devs = devices_snapshot();
@@ -229,7 +231,7 @@ int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, s
 
 // Batched small sequences: the batch is cut into runs of consecutive sequences of about equal total length, one run per
 // device (the sequences are pageable host memory as a rule, so at most CN_FANOUT_PAGEABLE_MAX devices are used).
-int host_batch(bool encode, const void *const *in, const size_t *lens, size_t count, void *const *out)
+int host_batch_impl(bool encode, const void *const *in, const size_t *lens, size_t count, void *const *out)
 {
     const std::vector<int> devs = devices_snapshot();
     size_t total = 0;
@@ -256,6 +258,24 @@ int host_batch(bool encode, const void *const *in, const size_t *lens, size_t co
         first = last;
     }
     return run_fanned_out(jobs, devs);
+}
+
+// Nothing may unwind across the C ABI: the host paths allocate (job lists, task queues, plans), so an allocation failure is
+// turned into a status here.
+template <class F> int no_throw(F &&body) noexcept
+{
+    try { return body(); }
+    catch (const std::bad_alloc &) { return fail(CN_ERR_NOMEM, "host memory allocation failed"); }
+    catch (const std::exception &e) { return fail(CN_ERR_CUDA, "internal error: %s", e.what()); }
+    catch (...) { return fail(CN_ERR_CUDA, "internal error"); }
+}
+int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, size_t len, const HostMode &mode = HostMode{}) noexcept
+{
+    return no_throw([&] { return host_codec_impl(cd, encode, src, dst, len, mode); });
+}
+int host_batch(bool encode, const void *const *in, const size_t *lens, size_t count, void *const *out) noexcept
+{
+    return no_throw([&] { return host_batch_impl(encode, in, lens, count, out); });
 }
 
 // ---- device-resident shards, one per device, single process ---------------------------------------------

@@ -171,16 +171,11 @@ encode_segmented_kernel(const uint8_t *__restrict__ n, const uint64_t *__restric
         for (int k = 0; k < 9; k++) u[k] = (wsel & 1u) ? t[k + 1] : t[k];
 #pragma unroll
         for (int k = 0; k < 8; k++) x[k] = __funnelshift_r(u[k], u[k + 1], shift);
-        // bytes at and beyond `avail` belong to the next sequence (or to nobody): they encode as 0, like the zeroed word of
-        // n_to_bits_lut (src/n_to_bits.rs:35)
-        if (avail < 32) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const int keep = (int)avail - 4 * k;                     // valid bytes of register k
-                x[k] = keep >= 4 ? x[k] : (keep <= 0 ? 0u : (x[k] & ((1u << (8 * keep)) - 1u)));
-            }
-        }
-        st_stream8(out + w0 + i, pack16(x[0], x[1], x[2], x[3]), pack16(x[4], x[5], x[6], x[7]));
+        // bytes at and beyond `avail` belong to the next sequence (or to nobody): their codes are cleared in the packed word,
+        // which leaves exactly the zeroed high bits of n_to_bits_lut's last word (src/n_to_bits.rs:35).  Branch-free: full and
+        // ragged words of a warp run the same instructions.
+        const uint64_t keep = avail >= 32 ? ~0ull : ((1ull << (2 * avail)) - 1ull);
+        st_stream8(out + w0 + i, pack16(x[0], x[1], x[2], x[3]) & (uint32_t)keep, pack16(x[4], x[5], x[6], x[7]) & (uint32_t)(keep >> 32));
     }
 }
 
