@@ -7,7 +7,7 @@ from .n_to_bits import (  # noqa: F401
     LengthError, bits_to_n_cuda, decode_device, encode_checked_device, encode_device, generate_device,
     generate_words_device, n_to_bits_checked_cuda, n_to_bits_cuda, words_for_len,
     ENC_COUNT, ENC_LUT_EXACT, ENC_PLAIN, encode_ex_device, n_to_bits_ex_cuda, n_to_bits_lut_cuda,
-    bits_to_n_batch_cuda, n_to_bits_batch_cuda, decode_segmented_device, encode_segmented_device, segment_word_offsets,
+    bits_to_n_batch_cuda, bits_to_n_cuda_async, n_to_bits_batch_cuda, n_to_bits_cuda_async, decode_segmented_device, encode_segmented_device, segment_word_offsets,
 )
 from .n_to_bits2 import (  # noqa: F401
     bits_to_n2_cuda, decode2_device, encode2_device, generate2_device, n_to_bits2_cuda, words2_for_len,

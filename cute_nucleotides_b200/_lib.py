@@ -30,6 +30,9 @@ PROTOTYPES = {
     "cn_bits_to_n_host": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p]),
     "cn_n_to_bits_host_batch": (c_int, [POINTER(c_void_p), POINTER(c_size_t), c_size_t, POINTER(c_void_p)]),
     "cn_bits_to_n_host_batch": (c_int, [POINTER(c_void_p), POINTER(c_size_t), c_size_t, POINTER(c_void_p)]),
+    "cn_n_to_bits_host_async": (c_int, [c_void_p, c_size_t, c_void_p, POINTER(c_void_p)]),
+    "cn_bits_to_n_host_async": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, POINTER(c_void_p)]),
+    "cn_wait": (c_int, [c_void_p]),
     "cn_encode_device": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "cn_decode_device": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
     "cn_encode_segmented_device": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p]),

@@ -112,6 +112,39 @@ int cn_bits_to_n_host_batch(const uint64_t *const *bits, const size_t *lens, siz
     return host_batch(false, reinterpret_cast<const void *const *>(bits), lens, count, reinterpret_cast<void *const *>(outs));
 }
 
+int cn_n_to_bits_host_async(const uint8_t *n, size_t len, uint64_t *out, cn_request **req)
+{
+    if (!req) return fail(CN_ERR_ARG, "cn_n_to_bits_host_async: null request pointer");
+    *req = nullptr;
+    if (len != 0 && (!n || !out)) return fail(CN_ERR_ARG, "cn_n_to_bits_host_async: null pointer");
+    return no_throw([&] {
+        Request *r = nullptr;
+        int rc = submit_async([=] { return len == 0 ? (int)CN_OK : host_codec(kCodec2bit, true, n, reinterpret_cast<uint8_t *>(out), len); }, &r);
+        *req = reinterpret_cast<cn_request *>(r);
+        return rc;
+    });
+}
+
+int cn_bits_to_n_host_async(const uint64_t *bits, size_t nwords, size_t len, uint8_t *out, cn_request **req)
+{
+    if (!req) return fail(CN_ERR_ARG, "cn_bits_to_n_host_async: null request pointer");
+    *req = nullptr;
+    if (len > (nwords << 5) || (nwords >> 59) != 0) return fail(CN_ERR_LENGTH, "%s", kPanicText);   // where the reference panics, up front
+    if (len != 0 && (!bits || !out)) return fail(CN_ERR_ARG, "cn_bits_to_n_host_async: null pointer");
+    return no_throw([&] {
+        Request *r = nullptr;
+        int rc = submit_async([=] { return len == 0 ? (int)CN_OK : host_codec(kCodec2bit, false, reinterpret_cast<const uint8_t *>(bits), out, len); }, &r);
+        *req = reinterpret_cast<cn_request *>(r);
+        return rc;
+    });
+}
+
+int cn_wait(cn_request *req)
+{
+    if (!req) return fail(CN_ERR_ARG, "cn_wait: null request");
+    return wait_request(reinterpret_cast<Request *>(req));
+}
+
 int cn_n_to_bits_checked_host(const uint8_t *n, size_t len, uint64_t *out, uint64_t *invalid_count)
 {
     if (!invalid_count) return fail(CN_ERR_ARG, "cn_n_to_bits_checked_host: null counter");

@@ -278,6 +278,100 @@ int host_batch(bool encode, const void *const *in, const size_t *lens, size_t co
     return no_throw([&] { return host_batch_impl(encode, in, lens, count, out); });
 }
 
+// ---- asynchronous host calls ------------------------------------------------------------------------------
+// cn_*_host_async hands the call to one of a few library threads (each with its own staging ring) and returns at once;
+// cn_wait collects the status.  A single-threaded caller can thus keep an encode and a decode in flight together -- the two
+// calls load opposite PCIe directions, so a stream of round trips runs at ~33 Gnt/s on one link instead of 26.5.
+struct Request {
+    std::mutex mu;
+    std::condition_variable cv;
+    bool done = false;
+    int rc = CN_OK;
+    char err[sizeof t_err] = "";
+    std::function<int()> work;
+    int device = -1;
+};
+
+class AsyncPool {
+public:
+    static AsyncPool &get()
+    {
+        static AsyncPool *pool = new AsyncPool();            // leaked on purpose, like the other pools
+        return *pool;
+    }
+    void submit(Request *r)
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            queue_.push_back(r);
+            // one thread per request in flight, up to kMax: spawn when more requests are queued than threads are idle
+            if ((int)queue_.size() > idle_ && threads_ < kMax) { threads_++; std::thread([this] { run(); }).detach(); }
+        }
+        cv_.notify_one();
+    }
+
+private:
+    static constexpr int kMax = 4;
+    void run()
+    {
+        for (;;) {
+            Request *r;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                idle_++;
+                cv_.wait(lk, [&] { return !queue_.empty(); });
+                idle_--;
+                r = queue_.front();
+                queue_.pop_front();
+            }
+            t_device = r->device;
+            int rc = r->work();
+            {
+                std::lock_guard<std::mutex> lk(r->mu);
+                r->rc = rc;
+                if (rc != CN_OK) { strncpy(r->err, t_err, sizeof r->err - 1); r->err[sizeof r->err - 1] = 0; }
+                r->done = true;
+            }
+            r->cv.notify_all();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<Request *> queue_;
+    int threads_ = 0, idle_ = 0;
+};
+
+// the device the calling thread would use right now: the one chosen with cn_init, else the current one
+int calling_device()
+{
+    if (t_device >= 0) return t_device;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return dev;
+}
+
+int submit_async(std::function<int()> work, Request **out)
+{
+    Request *r = new Request();
+    r->work = std::move(work);
+    r->device = calling_device();
+    *out = r;
+    AsyncPool::get().submit(r);
+    return CN_OK;
+}
+
+int wait_request(Request *r)
+{
+    {
+        std::unique_lock<std::mutex> lk(r->mu);
+        r->cv.wait(lk, [&] { return r->done; });
+    }
+    const int rc = r->rc;
+    if (rc != CN_OK) snprintf(t_err, sizeof t_err, "%s", r->err);
+    delete r;
+    return rc;
+}
+
 // ---- device-resident shards, one per device, single process ---------------------------------------------
 struct DeviceGuard {                        // launches happen on other devices; leave the caller's current device as it was
     int saved = -1;

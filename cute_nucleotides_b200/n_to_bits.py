@@ -21,7 +21,7 @@ from ._lib import LengthError, check
 
 __all__ = [
     "n_to_bits_cuda", "bits_to_n_cuda", "words_for_len", "n_to_bits_checked_cuda", "encode_checked_device",
-    "n_to_bits_lut_cuda", "n_to_bits_ex_cuda", "encode_ex_device", "n_to_bits_batch_cuda", "bits_to_n_batch_cuda",
+    "n_to_bits_lut_cuda", "n_to_bits_ex_cuda", "encode_ex_device", "n_to_bits_batch_cuda", "bits_to_n_batch_cuda", "n_to_bits_cuda_async", "bits_to_n_cuda_async",
     "encode_segmented_device", "decode_segmented_device", "segment_word_offsets",
     "encode_device", "decode_device", "generate_device", "generate_words_device", "LengthError",
     "ENC_PLAIN", "ENC_COUNT", "ENC_LUT_EXACT",
@@ -76,6 +76,39 @@ def n_to_bits_ex_cuda(n, mode: int):
 def n_to_bits_lut_cuda(n) -> np.ndarray:
     """Bit-exact n_to_bits_lut (src/n_to_bits.rs:34-47) on EVERY input, including bytes outside the alphabet (-> 0)."""
     return n_to_bits_ex_cuda(n, ENC_LUT_EXACT)[0]
+
+
+class AsyncResult:
+    """Handle of a cn_*_host_async call.  wait() blocks until the call is done and returns its result (a uint64 array for
+    an encode, bytes for a decode); it must be called exactly once.  The input is kept alive by the handle."""
+
+    def __init__(self, request, keep, result, finish):
+        self._request, self._keep, self._result, self._finish = request, keep, result, finish
+
+    def wait(self):
+        req, self._request = self._request, None
+        if req is None:
+            raise RuntimeError("wait() was already called on this request")
+        check(_lib.load().cn_wait(req))
+        return self._finish(self._result)
+
+
+def n_to_bits_cuda_async(n, out=None) -> AsyncResult:
+    """n_to_bits_cuda on a library thread (cn_n_to_bits_host_async): returns at once; .wait() yields the words."""
+    src = _as_u8(n)
+    res = np.empty(words_for_len(src.size), dtype=np.uint64) if out is None else out
+    req = ctypes.c_void_p()
+    check(_lib.load().cn_n_to_bits_host_async(src.ctypes.data, src.size, res.ctypes.data, ctypes.byref(req)))
+    return AsyncResult(req, src, res, lambda r: r)
+
+
+def bits_to_n_cuda_async(bits, length: int, out=None) -> AsyncResult:
+    """bits_to_n_cuda on a library thread (cn_bits_to_n_host_async): .wait() yields the bytes (or `out` when given)."""
+    words = np.ascontiguousarray(bits, dtype=np.uint64)
+    res = np.empty(length, dtype=np.uint8) if out is None else out
+    req = ctypes.c_void_p()
+    check(_lib.load().cn_bits_to_n_host_async(words.ctypes.data, words.size, length, res.ctypes.data, ctypes.byref(req)))
+    return AsyncResult(req, words, res, (lambda r: r.tobytes()) if out is None else (lambda r: r))
 
 
 def _ptr_array(a: np.ndarray):

@@ -85,6 +85,15 @@ CN_API int cn_bits_to_n_host(const uint64_t *bits, size_t nwords, size_t len, ui
 CN_API int cn_n_to_bits_host_batch(const uint8_t *const *seqs, const size_t *lens, size_t count, uint64_t *const *outs);
 CN_API int cn_bits_to_n_host_batch(const uint64_t *const *bits, const size_t *lens, size_t count, uint8_t *const *outs);
 
+/* Asynchronous flavours: the call runs on a library thread and `*req` receives a handle; cn_wait(req) blocks until it is
+ * done, returns ITS status (cn_last_error() then describes its failure) and releases the handle -- every request must be
+ * waited for exactly once, and the buffers must stay valid and untouched until then.  One encode and one decode in flight
+ * load the two PCIe directions at once (33 instead of 26.5 Gnt/s for a stream of round trips on one link). */
+typedef struct cn_request cn_request;
+CN_API int cn_n_to_bits_host_async(const uint8_t *n, size_t len, uint64_t *out, cn_request **req);
+CN_API int cn_bits_to_n_host_async(const uint64_t *bits, size_t nwords, size_t len, uint8_t *out, cn_request **req);
+CN_API int cn_wait(cn_request *req);
+
 /* ---- device-resident entry points (the roofline path; buffers already in HBM) ------------------ */
 /* `stream` is a cudaStream_t (NULL = default stream); launches are asynchronous on it, on the current
  * device.  d_n may have any alignment (16-byte aligned input takes the fast path); d_out must be 8-byte

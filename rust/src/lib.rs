@@ -36,10 +36,15 @@ pub mod ffi {
         pub fn cn_n_to_bits_host_batch(seqs: *const *const u8, lens: *const usize, count: usize, outs: *const *mut u64) -> c_int;
         pub fn cn_bits_to_n_host_batch(bits: *const *const u64, lens: *const usize, count: usize, outs: *const *mut u8) -> c_int;
         pub fn cn_set_devices(devices: *const c_int, count: c_int) -> c_int;
+        pub fn cn_n_to_bits_host_async(n: *const u8, len: usize, out: *mut u64, req: *mut *mut CnRequest) -> c_int;
+        pub fn cn_bits_to_n_host_async(bits: *const u64, nwords: usize, len: usize, out: *mut u8, req: *mut *mut CnRequest) -> c_int;
+        pub fn cn_wait(req: *mut CnRequest) -> c_int;
         pub fn cn_hamming_host(a: *const u64, b: *const u64, nwords: usize, len: usize, result: *mut u64) -> c_int;
         pub fn cn_reverse_complement_host(bits: *const u64, nwords: usize, len: usize, out: *mut u64) -> c_int;
     }
     pub const CN_ENC_LUT_EXACT: c_int = 2;
+    #[repr(C)]
+    pub struct CnRequest { _private: [u8; 0] }
 }
 
 fn fail(status: c_int) -> ! {
@@ -98,6 +103,46 @@ pub fn n_to_bits_cuda_batch(seqs: &[&[u8]]) -> Vec<Vec<u64>> {
         }
     }
     res
+}
+
+/// An encode running on a library thread; `wait()` returns the words.  Keeping one of these in flight while the previous
+/// batch is decoded loads both PCIe directions at once.
+pub struct PendingEncode<'a> {
+    req: *mut ffi::CnRequest,
+    res: Vec<u64>,
+    words: usize,
+    _input: std::marker::PhantomData<&'a [u8]>,
+}
+
+pub fn n_to_bits_cuda_async(n: &[u8]) -> PendingEncode<'_> {
+    let words = (n.len() >> 5) + if n.len() & 31 == 0 { 0 } else { 1 };
+    let mut res: Vec<u64> = Vec::with_capacity(words);
+    let mut req: *mut ffi::CnRequest = std::ptr::null_mut();
+    let status = unsafe { ffi::cn_n_to_bits_host_async(n.as_ptr(), n.len(), res.as_mut_ptr(), &mut req) };
+    if status != ffi::CN_OK {
+        fail(status);
+    }
+    PendingEncode { req, res, words, _input: std::marker::PhantomData }
+}
+
+impl<'a> PendingEncode<'a> {
+    pub fn wait(mut self) -> Vec<u64> {
+        let status = unsafe { ffi::cn_wait(self.req) };
+        self.req = std::ptr::null_mut();
+        if status != ffi::CN_OK {
+            fail(status);
+        }
+        unsafe { self.res.set_len(self.words) };
+        std::mem::take(&mut self.res)
+    }
+}
+
+impl<'a> Drop for PendingEncode<'a> {
+    fn drop(&mut self) {
+        if !self.req.is_null() {
+            unsafe { ffi::cn_wait(self.req) };      // the library still writes into `res`: never free it under a running call
+        }
+    }
 }
 
 /// Fan every later `*_cuda` call out over these GPUs (one PCIe link each); an empty slice restores single-GPU behaviour.
