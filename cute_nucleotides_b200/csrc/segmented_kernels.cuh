@@ -235,17 +235,18 @@ decode_segmented_kernel(const uint64_t *__restrict__ bits, const uint64_t *__res
     }
     __syncthreads();
     const uint32_t nvec = (uint32_t)((hi_addr - lo_addr) >> 4);
-    const uint64_t begin = a0 + sh.lo, end = a0 + sh.hi;                   // bytes this CTA owns
+    const uint32_t begin = (uint32_t)(a0 + sh.lo - lo_addr), end = (uint32_t)(a0 + sh.hi - lo_addr);   // tile bytes this CTA owns
     for (uint32_t v = threadIdx.x; v < nvec; v += kSegThreads) {
-        const uint64_t addr = lo_addr + 16ull * v;
-        const uint4 val = make_uint4(tile[seg_slot(4 * v)], tile[seg_slot(4 * v + 1)], tile[seg_slot(4 * v + 2)], tile[seg_slot(4 * v + 3)]);
-        if (addr >= begin && addr + 16 <= end) {
-            st_stream16(reinterpret_cast<void *>(addr), val);
-        } else {
+        const uint32_t *src = tile + 4 * v + (v >> 1);                    // = seg_slot(4 v); the vector's 4 words never straddle a pad
+        const uint4 val = make_uint4(src[0], src[1], src[2], src[3]);
+        uint8_t *dst = reinterpret_cast<uint8_t *>(lo_addr + 16ull * v);
+        if (16 * v >= begin && 16 * v + 16 <= end) {
+            st_stream16(dst, val);
+        } else {                                                          // the CTA's first / last vector is shared with a neighbour
             const uint32_t q4[4] = {val.x, val.y, val.z, val.w};
 #pragma unroll 1
-            for (int k = 0; k < 16; k++)
-                if (addr + k >= begin && addr + k < end) *reinterpret_cast<uint8_t *>(addr + k) = (uint8_t)(q4[k >> 2] >> (8 * (k & 3)));
+            for (uint32_t k = 0; k < 16; k++)
+                if (16 * v + k >= begin && 16 * v + k < end) dst[k] = (uint8_t)(q4[k >> 2] >> (8 * (k & 3)));
         }
     }
 }
