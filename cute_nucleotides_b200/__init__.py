@@ -11,7 +11,7 @@ from .n_to_bits import (  # noqa: F401
 )
 from .n_to_bits2 import (  # noqa: F401
     bits_to_n2_cuda, decode2_device, encode2_device, generate2_device, n_to_bits2_cuda, words2_for_len,
-    encode2_ex_device, n_to_bits2_ex_cuda, n_to_bits2_lut_cuda,
+    encode2_ex_device, n_to_bits2_ex_cuda, n_to_bits2_lut_cuda, bits_to_n2_batch_cuda, n_to_bits2_batch_cuda,
 )
 from .packed_ops import (  # noqa: F401
     complement_cuda, complement_device, hamming_cuda, hamming_device, reverse_complement_cuda, reverse_complement_device,

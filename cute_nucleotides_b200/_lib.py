@@ -64,6 +64,8 @@ PROTOTYPES = {
     "cn_words2_for_len": (c_size_t, [c_size_t]),
     "cn_n_to_bits2_host": (c_int, [c_void_p, c_size_t, c_void_p]),
     "cn_bits_to_n2_host": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p]),
+    "cn_n_to_bits2_host_batch": (c_int, [POINTER(c_void_p), POINTER(c_size_t), c_size_t, POINTER(c_void_p)]),
+    "cn_bits_to_n2_host_batch": (c_int, [POINTER(c_void_p), POINTER(c_size_t), c_size_t, POINTER(c_void_p)]),
     "cn_encode2_device": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "cn_decode2_device": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
     "cn_generate2_device": (c_int, [c_void_p, c_size_t, c_size_t, c_uint64, c_int, c_void_p]),

@@ -102,14 +102,28 @@ int cn_n_to_bits_host_batch(const uint8_t *const *seqs, const size_t *lens, size
 {
     if (count == 0) return CN_OK;
     if (!seqs || !lens || !outs) return fail(CN_ERR_ARG, "cn_n_to_bits_host_batch: null pointer");
-    return host_batch(true, reinterpret_cast<const void *const *>(seqs), lens, count, reinterpret_cast<void *const *>(outs));
+    return host_batch(kCodec2bit, true, reinterpret_cast<const void *const *>(seqs), lens, count, reinterpret_cast<void *const *>(outs));
 }
 
 int cn_bits_to_n_host_batch(const uint64_t *const *bits, const size_t *lens, size_t count, uint8_t *const *outs)
 {
     if (count == 0) return CN_OK;
     if (!bits || !lens || !outs) return fail(CN_ERR_ARG, "cn_bits_to_n_host_batch: null pointer");
-    return host_batch(false, reinterpret_cast<const void *const *>(bits), lens, count, reinterpret_cast<void *const *>(outs));
+    return host_batch(kCodec2bit, false, reinterpret_cast<const void *const *>(bits), lens, count, reinterpret_cast<void *const *>(outs));
+}
+
+int cn_n_to_bits2_host_batch(const uint8_t *const *seqs, const size_t *lens, size_t count, uint64_t *const *outs)
+{
+    if (count == 0) return CN_OK;
+    if (!seqs || !lens || !outs) return fail(CN_ERR_ARG, "cn_n_to_bits2_host_batch: null pointer");
+    return host_batch(kCodecBase5, true, reinterpret_cast<const void *const *>(seqs), lens, count, reinterpret_cast<void *const *>(outs));
+}
+
+int cn_bits_to_n2_host_batch(const uint64_t *const *bits, const size_t *lens, size_t count, uint8_t *const *outs)
+{
+    if (count == 0) return CN_OK;
+    if (!bits || !lens || !outs) return fail(CN_ERR_ARG, "cn_bits_to_n2_host_batch: null pointer");
+    return host_batch(kCodecBase5, false, reinterpret_cast<const void *const *>(bits), lens, count, reinterpret_cast<void *const *>(outs));
 }
 
 int cn_n_to_bits_host_async(const uint8_t *n, size_t len, uint64_t *out, cn_request **req)

@@ -540,6 +540,7 @@ int host_codec_one(const Codec &cd, bool encode, const uint8_t *src, uint8_t *ds
 // covers thousands of them.  Gather and scatter are spread over the copier pool; chunks flow through the same ring.
 // ------------------------------------------------------------------------------------------------
 struct BatchCtx {
+    unsigned group;                       // nucleotides per word: 32 (2-bit) or 27 (base-5)
     bool encode;
     const void *const *in;
     void *const *out;
@@ -554,11 +555,12 @@ void batch_gather(void *c, size_t a, size_t b)
         const size_t len = x.lens[i];
         if (!len) continue;
         if (x.encode) {
-            uint8_t *dst = x.pin_big + x.woff[i] * 32;
+            const size_t padded = (len + x.group - 1) / x.group * x.group;
+            uint8_t *dst = x.pin_big + x.woff[i] * x.group;
             memcpy(dst, x.in[i], len);
-            if (len & 31) memset(dst + len, 0, 32 - (len & 31));
+            if (padded > len) memset(dst + len, 0, padded - len);          // byte 0 -> code 0 / digit 0 in either codec
         } else {
-            memcpy(x.pin_small + x.woff[i] * 8, x.in[i], ((len + 31) >> 5) * 8);
+            memcpy(x.pin_small + x.woff[i] * 8, x.in[i], (len + x.group - 1) / x.group * 8);
         }
     }
 }
@@ -568,20 +570,19 @@ void batch_scatter(void *c, size_t a, size_t b)
     for (size_t i = a; i < b; i++) {
         const size_t len = x.lens[i];
         if (!len) continue;
-        if (x.encode) memcpy(x.out[i], x.pin_small + x.woff[i] * 8, ((len + 31) >> 5) * 8);
-        else memcpy(x.out[i], x.pin_big + x.woff[i] * 32, len);
+        if (x.encode) memcpy(x.out[i], x.pin_small + x.woff[i] * 8, (len + x.group - 1) / x.group * 8);
+        else memcpy(x.out[i], x.pin_big + x.woff[i] * x.group, len);
     }
 }
 
-int host_batch_one(bool encode, const void *const *in, const size_t *lens, size_t count, void *const *out)
+int host_batch_one(const Codec &cd, bool encode, const void *const *in, const size_t *lens, size_t count, void *const *out)
 {
     HostPipe &p = t_pipe;
     int rc = pipe_prepare(p);
     if (rc != CN_OK) return rc;
     CopyPool &pool = CopyPool::get();
-    const Codec &cd = kCodec2bit;
     const size_t stage = g_host_chunk_pageable.load(std::memory_order_relaxed);
-    const size_t stage_words = stage / 32;
+    const size_t stage_words = stage / 32;        // packed staging holds stage / 4 bytes; ASCII staging then needs <= stage bytes in either codec
 
     // plan: consecutive sequences are grouped into chunks of at most `stage` padded bytes; a sequence that does not fit a
     // chunk on its own goes through the ordinary streaming path afterwards
@@ -590,7 +591,7 @@ int host_batch_one(bool encode, const void *const *in, const size_t *lens, size_
     std::vector<size_t> woff(count), big;
     Chunk cur{0, 0, 0};
     for (size_t i = 0; i < count; i++) {
-        const size_t w = (lens[i] + 31) >> 5;
+        const size_t w = cd.words(lens[i]);
         if (lens[i] && (!in[i] || !out[i])) return fail(CN_ERR_ARG, "batch: null pointer for sequence %zu", i);
         if (w > stage_words) {
             big.push_back(i);
@@ -644,7 +645,7 @@ int host_batch_one(bool encode, const void *const *in, const size_t *lens, size_
             if (r != CN_OK) return r;
             pool.wait(sl.out_job);                                    // the slot's context is about to be rewritten
         }
-        ctx[k % kSlots] = BatchCtx{encode, in, out, lens, woff.data(), sl.pin_big, sl.pin_small};
+        ctx[k % kSlots] = BatchCtx{cd.group, encode, in, out, lens, woff.data(), sl.pin_big, sl.pin_small};
         post_ranges(sl.in_job, batch_gather, &ctx[k % kSlots], chunks[k]);
         return CN_OK;
     };
@@ -653,7 +654,7 @@ int host_batch_one(bool encode, const void *const *in, const size_t *lens, size_
         Slot &sl = p.slot[k % kSlots];
         if (k + 1 < nchunks && (rc = start_gather(k + 1)) != CN_OK) { first_error = rc; break; }
         pool.wait(sl.in_job);
-        const size_t words = chunks[k].words, nt = words * 32;
+        const size_t words = chunks[k].words, nt = words * cd.group;
         uint8_t *h_in = encode ? sl.pin_big : sl.pin_small, *h_out = encode ? sl.pin_small : sl.pin_big;
         uint8_t *d_in = encode ? sl.dev_big : sl.dev_small, *d_out = encode ? sl.dev_small : sl.dev_big;
         const size_t in_bytes = encode ? nt : words * 8, out_bytes = encode ? words * 8 : nt;

@@ -231,7 +231,7 @@ int host_codec_impl(const Codec &cd, bool encode, const uint8_t *src, uint8_t *d
 
 // Batched small sequences: the batch is cut into runs of consecutive sequences of about equal total length, one run per
 // device (the sequences are pageable host memory as a rule, so at most CN_FANOUT_PAGEABLE_MAX devices are used).
-int host_batch_impl(bool encode, const void *const *in, const size_t *lens, size_t count, void *const *out)
+int host_batch_impl(const Codec &cd, bool encode, const void *const *in, const size_t *lens, size_t count, void *const *out)
 {
     const std::vector<int> devs = devices_snapshot();
     size_t total = 0;
@@ -240,10 +240,10 @@ int host_batch_impl(bool encode, const void *const *in, const size_t *lens, size
     if (parts > devs.size()) parts = devs.size();
     if (parts > g_fan_pageable_max) parts = g_fan_pageable_max;
     if (devs.empty() || parts <= 1) {
-        if (devs.empty()) return host_batch_one(encode, in, lens, count, out);
+        if (devs.empty()) return host_batch_one(cd, encode, in, lens, count, out);
         std::vector<FanJob> one(1);
         one[0].live = true;
-        one[0].work = [=] { return host_batch_one(encode, in, lens, count, out); };
+        one[0].work = [=, &cd] { return host_batch_one(cd, encode, in, lens, count, out); };
         return run_fanned_out(one, devs);
     }
     std::vector<FanJob> jobs(parts);
@@ -254,7 +254,7 @@ int host_batch_impl(bool encode, const void *const *in, const size_t *lens, size
         while (last < count && (k + 1 == parts || acc + lens[last] <= target)) acc += lens[last++];
         const size_t n = last - first, at = first;
         jobs[k].live = n != 0;
-        jobs[k].work = [=] { return host_batch_one(encode, in + at, lens + at, n, out + at); };
+        jobs[k].work = [=, &cd] { return host_batch_one(cd, encode, in + at, lens + at, n, out + at); };
         first = last;
     }
     return run_fanned_out(jobs, devs);
@@ -273,9 +273,9 @@ int host_codec(const Codec &cd, bool encode, const uint8_t *src, uint8_t *dst, s
 {
     return no_throw([&] { return host_codec_impl(cd, encode, src, dst, len, mode); });
 }
-int host_batch(bool encode, const void *const *in, const size_t *lens, size_t count, void *const *out) noexcept
+int host_batch(const Codec &cd, bool encode, const void *const *in, const size_t *lens, size_t count, void *const *out) noexcept
 {
-    return no_throw([&] { return host_batch_impl(encode, in, lens, count, out); });
+    return no_throw([&] { return host_batch_impl(cd, encode, in, lens, count, out); });
 }
 
 // ---- asynchronous host calls ------------------------------------------------------------------------------

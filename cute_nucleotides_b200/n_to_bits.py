@@ -115,15 +115,12 @@ def _ptr_array(a: np.ndarray):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_void_p))
 
 
-def n_to_bits_batch_cuda(buf, offsets, out=None):
-    """Encode many independent sequences in ONE call (cn_n_to_bits_host_batch).  Sequence i is buf[offsets[i]:offsets[i+1]]
-    (offsets: count+1 non-decreasing integers).  Returns (words, word_offsets): sequence i's packed words -- exactly what
-    n_to_bits_cuda(sequence i) returns -- are words[word_offsets[i]:word_offsets[i+1]].  `out`: a uint64 array to reuse."""
+def _encode_batch(buf, offsets, out, group, fn):
     src = _as_u8(buf)
     offs = np.ascontiguousarray(offsets, dtype=np.uint64)
     count = offs.size - 1
     lens = np.ascontiguousarray(np.diff(offs))
-    wcount = (lens + np.uint64(31)) >> np.uint64(5)
+    wcount = (lens + np.uint64(group - 1)) // np.uint64(group)
     woffs = np.zeros(count + 1, dtype=np.uint64)
     np.cumsum(wcount, out=woffs[1:])
     words = np.empty(int(woffs[-1]), dtype=np.uint64) if out is None else out[: int(woffs[-1])]
@@ -132,18 +129,16 @@ def n_to_bits_batch_cuda(buf, offsets, out=None):
     in_ptrs = np.uint64(src.ctypes.data) + offs[:-1]
     out_ptrs = np.uint64(words.ctypes.data) + woffs[:-1] * np.uint64(8)
     lens_c = lens.ctypes.data_as(ctypes.POINTER(ctypes.c_size_t))
-    check(_lib.load().cn_n_to_bits_host_batch(_ptr_array(in_ptrs), lens_c, count, _ptr_array(out_ptrs)))
+    check(fn(_ptr_array(in_ptrs), lens_c, count, _ptr_array(out_ptrs)))
     return words, woffs
 
 
-def bits_to_n_batch_cuda(words, word_offsets, lengths, out=None):
-    """Inverse of n_to_bits_batch_cuda: returns (buf, offsets) with sequence i at buf[offsets[i]:offsets[i+1]].
-    `out`: a uint8 array to reuse."""
+def _decode_batch(words, word_offsets, lengths, out, group, fn):
     w = np.ascontiguousarray(words, dtype=np.uint64)
     woffs = np.ascontiguousarray(word_offsets, dtype=np.uint64)
     lens = np.ascontiguousarray(lengths, dtype=np.uint64)
     count = lens.size
-    if np.any(lens > (np.diff(woffs) << np.uint64(5))):
+    if np.any(lens > np.diff(woffs) * np.uint64(group)):
         raise LengthError(_lib.CN_ERR_LENGTH, _lib.load().cn_length_panic_message().decode())
     offs = np.zeros(count + 1, dtype=np.uint64)
     np.cumsum(lens, out=offs[1:])
@@ -153,8 +148,21 @@ def bits_to_n_batch_cuda(words, word_offsets, lengths, out=None):
     in_ptrs = np.uint64(w.ctypes.data) + woffs[:-1] * np.uint64(8)
     out_ptrs = np.uint64(out.ctypes.data) + offs[:-1]
     lens_c = lens.ctypes.data_as(ctypes.POINTER(ctypes.c_size_t))
-    check(_lib.load().cn_bits_to_n_host_batch(_ptr_array(in_ptrs), lens_c, count, _ptr_array(out_ptrs)))
+    check(fn(_ptr_array(in_ptrs), lens_c, count, _ptr_array(out_ptrs)))
     return out, offs
+
+
+def n_to_bits_batch_cuda(buf, offsets, out=None):
+    """Encode many independent sequences in ONE call (cn_n_to_bits_host_batch).  Sequence i is buf[offsets[i]:offsets[i+1]]
+    (offsets: count+1 non-decreasing integers).  Returns (words, word_offsets): sequence i's packed words -- exactly what
+    n_to_bits_cuda(sequence i) returns -- are words[word_offsets[i]:word_offsets[i+1]].  `out`: a uint64 array to reuse."""
+    return _encode_batch(buf, offsets, out, 32, _lib.load().cn_n_to_bits_host_batch)
+
+
+def bits_to_n_batch_cuda(words, word_offsets, lengths, out=None):
+    """Inverse of n_to_bits_batch_cuda: returns (buf, offsets) with sequence i at buf[offsets[i]:offsets[i+1]].
+    `out`: a uint8 array to reuse."""
+    return _decode_batch(words, word_offsets, lengths, out, 32, _lib.load().cn_bits_to_n_host_batch)
 
 
 def bits_to_n_cuda(bits, length: int) -> bytes:

@@ -14,10 +14,10 @@ import numpy as np
 
 from . import _lib
 from ._lib import LengthError, check
-from .n_to_bits import _as_u8, _stream_ptr
+from .n_to_bits import _as_u8, _decode_batch, _encode_batch, _stream_ptr
 
 __all__ = ["n_to_bits2_cuda", "bits_to_n2_cuda", "words2_for_len", "encode2_device", "decode2_device", "generate2_device",
-           "n_to_bits2_ex_cuda", "n_to_bits2_lut_cuda", "encode2_ex_device"]
+           "n_to_bits2_ex_cuda", "n_to_bits2_lut_cuda", "encode2_ex_device", "n_to_bits2_batch_cuda", "bits_to_n2_batch_cuda"]
 
 
 def words2_for_len(length: int) -> int:
@@ -47,6 +47,15 @@ def n_to_bits2_ex_cuda(n, mode: int):
 def n_to_bits2_lut_cuda(n) -> np.ndarray:
     """Bit-exact n_to_bits2_lut (src/n_to_bits2.rs:37-74) on every input."""
     return n_to_bits2_ex_cuda(n, _lib.CN_ENC_LUT_EXACT)[0]
+
+
+def n_to_bits2_batch_cuda(buf, offsets, out=None):
+    """Many independent sequences in ONE call (cn_n_to_bits2_host_batch); see n_to_bits_batch_cuda.  27 nucleotides per word."""
+    return _encode_batch(buf, offsets, out, 27, _lib.load().cn_n_to_bits2_host_batch)
+
+
+def bits_to_n2_batch_cuda(words, word_offsets, lengths, out=None):
+    return _decode_batch(words, word_offsets, lengths, out, 27, _lib.load().cn_bits_to_n2_host_batch)
 
 
 def bits_to_n2_cuda(bits, length: int) -> bytes:

@@ -199,6 +199,10 @@ CN_API size_t cn_words2_for_len(size_t len);
 CN_API int cn_n_to_bits2_host(const uint8_t *n, size_t len, uint64_t *out);
 /* bits_to_n2_{lut,pdep}(bits, len) -- src/n_to_bits2.rs:78, 196.  CN_ERR_LENGTH when len > 27 * nwords (:79-81). */
 CN_API int cn_bits_to_n2_host(const uint64_t *bits, size_t nwords, size_t len, uint8_t *out);
+/* Many independent sequences in one call, like cn_n_to_bits_host_batch: element i == cn_n_to_bits2_host on sequence i
+ * (cn_words2_for_len(lens[i]) words each). */
+CN_API int cn_n_to_bits2_host_batch(const uint8_t *const *seqs, const size_t *lens, size_t count, uint64_t *const *outs);
+CN_API int cn_bits_to_n2_host_batch(const uint64_t *const *bits, const size_t *lens, size_t count, uint8_t *const *outs);
 /* Device-resident pair; the ASCII side takes the tiled fast path when 16-byte aligned. */
 CN_API int cn_encode2_device(const void *d_n, size_t len, void *d_out, void *stream);
 CN_API int cn_decode2_device(const void *d_bits, size_t nwords, size_t len, void *d_out, void *stream);

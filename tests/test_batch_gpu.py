@@ -88,6 +88,32 @@ def test_batch_fans_out_over_the_device_set(cn, oracle):
         cn.set_devices([])
 
 
+def test_batch_base5(cn, oracle):
+    """The same batched calls for the base-5 codec (27 nucleotides per word): per sequence == n_to_bits2_lut / bits_to_n2_lut
+    (src/n_to_bits2.rs:37-107), incl. ragged triplets, empty sequences and sequences longer than a staging chunk."""
+    from cute_nucleotides_b200 import _lib
+    rng = np.random.default_rng(21)
+    for lens in ([5, 35, 0, 27, 28, 1, 2, 26, 54, 55, 40000], rng.integers(1, 400, size=30000), [3456 * 3 + 1] * 50):
+        lens = np.asarray(lens, dtype=np.uint64)
+        offs = np.zeros(lens.size + 1, dtype=np.uint64)
+        np.cumsum(lens, out=offs[1:])
+        buf = oracle.generate2(int(offs[-1]), seed=int(lens.size), alphabet=12)
+        words, woffs = cn.n_to_bits2_batch_cuda(buf, offs)
+        for i in (range(lens.size) if lens.size <= 100 else rng.choice(lens.size, 300, replace=False)):
+            s, e = int(offs[i]), int(offs[i + 1])
+            assert np.array_equal(words[int(woffs[i]): int(woffs[i + 1])], oracle.n_to_bits2(buf[s:e], "lut")), (i, e - s)
+        out, ooffs = cn.bits_to_n2_batch_cuda(words, woffs, lens)
+        assert np.array_equal(ooffs, offs) and out.tobytes() == oracle.canonical2(buf)
+    _lib.check(_lib.load().cn_set_host_chunks(0, 64 << 10))
+    lens = np.asarray([100, 100000, 5, 70000, 27 * 2048, 27 * 2048 + 1, 31], dtype=np.uint64)
+    offs = np.zeros(lens.size + 1, dtype=np.uint64)
+    np.cumsum(lens, out=offs[1:])
+    buf = oracle.generate2(int(offs[-1]), seed=3, alphabet=12)
+    words, woffs = cn.n_to_bits2_batch_cuda(buf, offs)
+    assert np.array_equal(words, np.concatenate([oracle.n_to_bits2(buf[int(offs[i]): int(offs[i + 1])], "lut") for i in range(lens.size)]))
+    assert cn.bits_to_n2_batch_cuda(words, woffs, lens)[0].tobytes() == oracle.canonical2(buf)
+
+
 def test_batch_from_threads(cn, oracle):
     import threading
     errors = []
