@@ -17,6 +17,7 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#include <cerrno>
 #include <sys/mman.h>
 #include <immintrin.h>
 
@@ -199,6 +200,22 @@ private:
     std::deque<Task> queue_;
     std::atomic<int> started_{0};
 };
+
+// A large pageable destination is usually a freshly allocated Vec whose pages have never been touched: left alone, every
+// 4 KiB page faults separately inside the copy-out loop (the C++ mirror measured 1 GiB decodes at 14-17 GiB/s into a fresh
+// vector vs 35+ into a touched one).  MADV_POPULATE_WRITE (Linux >= 5.14) faults a whole range in with one call; the pool
+// runs it for chunk k's destination while chunk k is still on the GPU.  Content is never modified.
+#ifndef MADV_POPULATE_WRITE
+#define MADV_POPULATE_WRITE 23
+#endif
+std::atomic<bool> g_populate_ok{true};
+void populate_range(void *, size_t begin, size_t end)
+{
+    if (!g_populate_ok.load(std::memory_order_relaxed)) return;
+    const size_t lo = begin & ~(size_t)4095, hi = (end + 4095) & ~(size_t)4095;
+    if (madvise(reinterpret_cast<void *>(lo), hi - lo, MADV_POPULATE_WRITE) != 0 && errno == EINVAL)
+        g_populate_ok.store(false, std::memory_order_relaxed);           // kernel too old: stop asking
+}
 
 // ------------------------------------------------------------------------------------------------
 // host-slice pipeline.  Per calling thread and device: kSlots slots, each with its own stream, a pinned and a
@@ -423,6 +440,8 @@ int host_codec_one(const Codec &cd, bool encode, const uint8_t *src, uint8_t *ds
         if (hi > lo) (void)madvise(reinterpret_cast<void *>(lo), hi - lo, MADV_HUGEPAGE);
     }
 
+    const bool populate = !dst_pinned && dst_bytes >= ((size_t)8 << 20) && g_populate_ok.load(std::memory_order_relaxed);
+
     const size_t nchunks = (len + chunk - 1) / chunk;
     const int slots_used = nchunks < (size_t)kSlots ? (int)nchunks : kSlots;
     for (int k = 0; k < slots_used; k++) {
@@ -511,6 +530,7 @@ int host_codec_one(const Codec &cd, bool encode, const uint8_t *src, uint8_t *ds
         if (e != cudaSuccess) rc = fail(CN_ERR_CUDA, "host pipeline: submitting chunk %zu failed: %s", k, cudaGetErrorString(e));
         if (rc != CN_OK) { first_error = rc; break; }
         issued = k + 1;
+        if (populate) pool.post_fn(sl.out_job, populate_range, nullptr, {addr(dst + g.out_off), addr(dst + g.out_off) + g.out_bytes});
     }
 
     // drain: wait for what is in flight, finish the copies (also on the error path: nothing may still be running into
